@@ -1,0 +1,109 @@
+"""ctypes binding of libsvt_b200.so (include/svt_b200.h).  Fails loudly: there is no fallback path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvt_b200.so")
+
+MAX_CONV_LAYERS = 8
+
+
+class EncoderConfig(C.Structure):
+    _fields_ = [
+        ("hidden_size", C.c_int), ("num_layers", C.c_int), ("num_heads", C.c_int), ("ffn_size", C.c_int),
+        ("num_conv_layers", C.c_int), ("conv_dim", C.c_int),
+        ("conv_kernel", C.c_int * MAX_CONV_LAYERS), ("conv_stride", C.c_int * MAX_CONV_LAYERS),
+        ("conv_bias", C.c_int), ("feat_norm_layer", C.c_int), ("stable_layer_norm", C.c_int),
+        ("pos_conv_kernel", C.c_int), ("pos_conv_groups", C.c_int), ("layer_norm_eps", C.c_float),
+        ("normalize_wav", C.c_int), ("output_norm", C.c_int),
+    ]
+
+
+class FusionConfig(C.Structure):
+    _fields_ = [("d_model", C.c_int), ("nhead", C.c_int), ("d_ffn", C.c_int), ("alpha", C.c_float)]
+
+
+class SvtError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libsvt_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+_P = C.c_void_p
+_SIGS = {
+    "svt_version": (C.c_int, []),
+    "svt_last_error": (C.c_char_p, []),
+    "svt_device_count": (C.c_int, []),
+    "svt_encoder_create": (C.c_int, [C.POINTER(EncoderConfig), C.POINTER(_P)]),
+    "svt_encoder_destroy": (None, [_P]),
+    "svt_encoder_set_tensor": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, C.c_int]),
+    "svt_encoder_set_head": (C.c_int, [_P, _P, _P, C.c_int]),
+    "svt_encoder_finalize": (C.c_int, [_P]),
+    "svt_encoder_num_frames": (C.c_int, [_P, C.c_int]),
+    "svt_encoder_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
+    "svt_encoder_forward": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P, _P, _P]),
+    "svt_encoder_forward_host": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P, _P, _P, _P]),
+    "svt_fusion_create": (C.c_int, [C.POINTER(FusionConfig), C.POINTER(_P)]),
+    "svt_fusion_destroy": (None, [_P]),
+    "svt_fusion_set_tensor": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, C.c_int]),
+    "svt_fusion_finalize": (C.c_int, [_P]),
+    "svt_fusion_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
+    "svt_fusion_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P, _P]),
+    "svt_frame_postproc": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "svt_frame2note": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_double, C.c_double, C.c_double, _P, C.c_int,
+                                 C.POINTER(C.c_int)]),
+    "svt_op_gemm": (C.c_int, [_P, C.c_longlong, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
+                              C.c_int, _P]),
+    "svt_op_posconv": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "svt_op_pack_posconv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "svt_op_attention": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "svt_op_layer_norm": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
+    "svt_op_linear_small": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P]),
+    "svt_op_conv0": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built -- never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m svt_speechbrain_b200.build` "
+                "(there is no CPU / PyTorch fallback for this package)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise SvtError(status, lib().svt_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Raw address of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream_ptr():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what}: expected a CUDA tensor -- svt_speechbrain_b200 is a B200 (sm_100a) implementation "
+            "with no CPU fallback")

@@ -1,0 +1,123 @@
+"""AMT inference pipeline around the reference-shaped modules: wav -> lobe -> head -> per-frame
+sigmoid / argmax -> frame2note, i.e. `AMT.compute_forward` + the evaluation half of `AMT.compute_objectives`
+(MIR_ST500/train_audio_ssl.py:28-48, 85-108), with the reference's one-utterance-at-a-time loop replaced by
+batched clips and with song chunking as in the recipes' dataio (prepare_benchmarks.py:117-130,
+train_audio_ssl.py:373-390).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from ._lib import check, current_stream_ptr, lib, ptr
+from .utils import decode_arrays
+
+
+@dataclass
+class AMTHparams:
+    """Scalars of MIR_ST500/hparams/train_audio_ssl.yaml that the inference path reads."""
+
+    sample_rate: int = 16000
+    frame_rate: float = 49.8
+    dur_threshold: float = 5.0
+    onset_threshold: float = 0.4
+    offset_threshold: float = 0.5
+    pitch_octave_num: int = 4
+    pitch_class_num: int = 12
+
+    @property
+    def n_out(self) -> int:
+        return 2 + (self.pitch_octave_num + 1) + (self.pitch_class_num + 1)
+
+
+def split_song(n_samples: int, hp: AMTHparams, dur: Optional[float] = None) -> List[Tuple[int, int]]:
+    """Sample ranges of a song's utterances, reference rule: utter_num = round(duration / dur); utterance i
+    (1-based) covers [round((i-1)*sr*dur), round(i*sr*dur)), the last one takes the remainder."""
+    dur = hp.dur_threshold if dur is None else dur
+    duration = n_samples / hp.sample_rate
+    utter_num = max(int(round(duration / dur)), 1)
+    out = []
+    for i in range(1, utter_num + 1):
+        a = round((i - 1) * hp.sample_rate * dur)
+        b = n_samples if i == utter_num else round(i * hp.sample_rate * dur)
+        out.append((a, b))
+    return out
+
+
+class AMTTranscriber:
+    """lobe: svt_speechbrain_b200.HuggingFaceWav2Vec2; head: svt_speechbrain_b200.Linear (n_neurons = 20)."""
+
+    def __init__(self, lobe, head, hparams: Optional[AMTHparams] = None, device="cuda"):
+        self.lobe, self.head = lobe, head
+        self.hp = hparams or AMTHparams()
+        self.device = torch.device(device)
+        if self.head.w.weight.shape[0] != self.hp.n_out:
+            raise ValueError(f"head has {self.head.w.weight.shape[0]} outputs, hparams imply {self.hp.n_out}")
+        self._head_key = None
+
+    def _engine(self):
+        eng = self.lobe.engine(self.device)
+        key = (id(eng), self.head.w.weight.data_ptr(), self.head.w.weight._version,
+               None if self.head.w.bias is None else self.head.w.bias._version)
+        if self._head_key != key:
+            eng.set_head(self.head.w.weight, self.head.w.bias)
+            self._head_key = key
+        return eng
+
+    @torch.no_grad()
+    def logits(self, wav: torch.Tensor) -> torch.Tensor:
+        """wav (B, L) CUDA fp32 -> frame logits (B, T, 20) CUDA fp32 (encoder + output norm + head fused)."""
+        _, lg = self._engine().forward(wav, want_feats=False, want_logits=True)
+        return lg
+
+    def frame_info(self, logits: torch.Tensor):
+        """(n_frames, 20) CUDA logits -> host arrays (p_on f32, p_off f32, octave i32, pitch_class i32).
+        argmax runs on the device (first max wins); the two sigmoids are taken on the HOST with torch so the
+        probabilities are bit-identical to the CPU reference that frame2note's `==` / `>=` tests see."""
+        lg = logits.reshape(-1, logits.shape[-1]).contiguous()
+        n = lg.shape[0]
+        octv = torch.empty(n, dtype=torch.int32, device=lg.device)
+        pc = torch.empty(n, dtype=torch.int32, device=lg.device)
+        hp = self.hp
+        with torch.cuda.device(lg.device):
+            check(lib().svt_frame_postproc(ptr(lg), n, lg.shape[1], 2, hp.pitch_octave_num + 1,
+                                           2 + hp.pitch_octave_num + 1, hp.pitch_class_num + 1, ptr(octv), ptr(pc),
+                                           current_stream_ptr()))
+        on_off = lg[:, :2].cpu()
+        p = torch.sigmoid(on_off)
+        return p[:, 0].contiguous().numpy(), p[:, 1].contiguous().numpy(), octv.cpu().numpy(), pc.cpu().numpy()
+
+    def decode(self, logits: torch.Tensor) -> np.ndarray:
+        """(n_frames, 20) logits of ONE song (utterances already concatenated in order) -> (n_notes, 3) float64."""
+        p_on, p_off, octv, pc = self.frame_info(logits)
+        return decode_arrays(p_on, p_off, octv, pc, self.hp.onset_threshold, self.hp.offset_threshold,
+                             1.0 / self.hp.frame_rate)
+
+    @torch.no_grad()
+    def transcribe_song(self, wav: torch.Tensor, dur: Optional[float] = None, batch_clips: int = 64,
+                        per_clip_norm: bool = True) -> np.ndarray:
+        """wav: 1-D waveform of a whole song.  Utterances are cut by the reference rule, run through the
+        encoder, concatenated in order and decoded once.  per_clip_norm=True reproduces the reference
+        evaluation loop (batch size 1: the whole-tensor norms see one utterance at a time); equal-length
+        utterances are still batched on the device, one forward per utterance only when per_clip_norm."""
+        wav = wav.to(self.device, torch.float32).reshape(-1)
+        spans = split_song(wav.numel(), self.hp, dur)
+        pieces: List[torch.Tensor] = []
+        if per_clip_norm:
+            for a, b in spans:
+                pieces.append(self.logits(wav[a:b].unsqueeze(0))[0])
+        else:
+            i = 0
+            while i < len(spans):
+                j = i
+                L = spans[i][1] - spans[i][0]
+                while j < len(spans) and j - i < batch_clips and spans[j][1] - spans[j][0] == L:
+                    j += 1
+                clips = torch.stack([wav[a:b] for a, b in spans[i:j]])
+                lg = self.logits(clips)
+                pieces.extend(lg[k] for k in range(lg.shape[0]))
+                i = j
+        return self.decode(torch.cat(pieces, dim=0))

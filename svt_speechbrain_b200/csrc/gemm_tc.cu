@@ -1,0 +1,360 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma
+// (128 x BN x 16, fp32 accumulators in TMEM, double-buffered) -> tcgen05.ld epilogue with fused
+// bias / GELU / ReLU / fp32 residual and bf16 or fp32 stores.
+//
+// Roles (384 threads, 1 CTA per SM):
+//   warp 0      : TMA producer (one elected lane)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane)
+//   warps 2-3   : idle (keep the epilogue warps aligned to TMEM lane quadrants: warp_id % 4)
+//   warps 4-11  : epilogue; warp w owns TMEM lanes 32*(w%4).. and column half (w-4)/4 of the tile
+#include "gemm_tc.cuh"
+
+#include <mutex>
+
+namespace svt {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kNumEpiWarps = 8;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator stages (power of two)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct KParams {
+  int mode, M, N, K, k_inner;
+  int n_tiles, m_tiles, num_kb;
+  int tiles_per_clip, clip_rows, clip_valid, pad_left;
+  int n_stride;  // output-column (and posconv input-channel) offset per n-tile
+  int n_valid;   // valid output columns per n-tile (<= BN)
+  const float* bias;
+  const float* resid;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  int ld_out, act;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms need 1024-byte aligned tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kNumEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + C::kABytes;
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          if (p.mode == 0) {
+            const int k0 = kb * BK;
+            tma_load_3d(sa, &tmA, &full_bar[stage], k0 % p.k_inner, k0 / p.k_inner, m_tile * BM);
+            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n_tile * BN);
+          } else {
+            // positional conv: group = n_tile, tap = kb; frames shifted by (tap - pad_left), OOB -> 0
+            const int clip = m_tile / p.tiles_per_clip;
+            const int tt = m_tile % p.tiles_per_clip;
+            tma_load_3d(sa, &tmA, &full_bar[stage], n_tile * p.n_stride, tt * BM + kb - p.pad_left, clip);
+            tma_load_2d(sb, &tmB, &full_bar[stage], 0, (n_tile * p.num_kb + kb) * BN);
+          }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint64_t da = make_sw128_kmajor_desc(sa);
+          const uint64_t db = make_sw128_kmajor_desc(sa + C::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in 16-byte units
+            umma_bf16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------------ epilogue
+    const int quad = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;
+    constexpr int kColsPerWarp = BN / 2;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      int row0, valid;
+      if (p.mode == 0) {
+        row0 = m_tile * BM;
+        valid = p.M - row0;
+      } else {
+        const int clip = m_tile / p.tiles_per_clip;
+        const int tt = m_tile % p.tiles_per_clip;
+        row0 = clip * p.clip_rows + tt * BM;
+        valid = p.clip_valid - tt * BM;
+      }
+      const int r_in_tile = quad * 32 + lane;
+      const bool row_ok = r_in_tile < valid;
+      const size_t row = static_cast<size_t>(row0 + r_in_tile);
+
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < kColsPerWarp; c += 32) {
+        const int col_in_tile = half * kColsPerWarp + c;
+        const int col = n_tile * p.n_stride + col_in_tile;
+        const int nv = p.n_valid - col_in_tile;  // valid columns of this 32-wide chunk
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN + col_in_tile),
+                  r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (4 * j < nv) {
+              const float4 b = __ldg(b4 + j);
+              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+        }
+        if (p.act == kActGelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (p.act == kActRelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        if (row_ok) {
+          const size_t off = row * static_cast<size_t>(p.ld_out) + static_cast<size_t>(col);
+          if (p.resid != nullptr) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.resid + off);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (4 * j < nv) {
+                const float4 q = r4[j];
+                v[4 * j + 0] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+              }
+            }
+          }
+          if (p.out_f32 != nullptr) {
+            float4* o4 = reinterpret_cast<float4*>(p.out_f32 + off);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (4 * j < nv) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (p.out_bf16 != nullptr) {
+            uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (8 * j < nv)
+                o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                     pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          }
+        }
+      }
+      // all of this warp's TMEM reads are complete (wait::ld above) -> release the accumulator stage
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                    const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return fail(kCudaError, "cuTensorMapEncodeTiled entry point not available (no driver?)");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_elems[i - 1] * 2;
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+                  gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    std::string s = "cuTensorMapEncodeTiled failed, code " + std::to_string(static_cast<int>(r)) + " rank " +
+                    std::to_string(rank) + " dims";
+    for (int i = 0; i < rank; ++i) s += " " + std::to_string(dims[i]);
+    s += " strides";
+    for (int i = 0; i + 1 < rank; ++i) s += " " + std::to_string(strides_elems[i]);
+    return fail(kCudaError, s);
+  }
+  return kOk;
+}
+
+template <int BN>
+int launch(const GemmArgs& g, const KParams& kp, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  CUtensorMap tmA, tmB;
+  uint32_t abox[3];
+  if (g.mode == 0) { abox[0] = BK; abox[1] = 1; abox[2] = BM; } else { abox[0] = BK; abox[1] = BM; abox[2] = 1; }
+  SVT_TRY(encode_bf16_map(&tmA, g.a, 3, g.a_dims, g.a_strides, abox));
+  const uint64_t wd[2] = {static_cast<uint64_t>(g.w_cols), static_cast<uint64_t>(g.w_rows)};
+  const uint64_t ws[1] = {static_cast<uint64_t>(g.w_cols)};
+  const uint32_t wb[2] = {BK, BN};
+  SVT_TRY(encode_bf16_map(&tmB, g.w, 2, wd, ws, wb));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SVT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = kp.m_tiles * kp.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, kp);
+  SVT_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace
+
+int gemm_bf16_tc(const GemmArgs& g, cudaStream_t stream) {
+  KParams kp{};
+  kp.mode = g.mode;
+  kp.M = g.M;
+  kp.N = g.N;
+  kp.K = g.K;
+  kp.k_inner = g.k_inner > 0 ? g.k_inner : g.K;
+  kp.bias = g.bias;
+  kp.resid = g.resid;
+  kp.out_f32 = g.out_f32;
+  kp.out_bf16 = g.out_bf16;
+  kp.ld_out = g.ld_out;
+  kp.act = g.act;
+  if (g.mode == 0 && (g.K % BK != 0 || kp.k_inner % BK != 0))
+    return fail(kInvalidArgument, "gemm: K must be a multiple of 64");
+  if (g.ld_out % 8 != 0) return fail(kInvalidArgument, "gemm: ld_out must be a multiple of 8");
+  int bn;
+  if (g.mode == 1) {
+    bn = 64;
+    if (g.group_size <= 0 || g.group_size > 64 || g.group_size % 8 != 0 || g.N % g.group_size != 0)
+      return fail(kInvalidArgument, "posconv: channels per group must be a multiple of 8 and <= 64");
+    kp.tiles_per_clip = ceil_div(g.clip_valid, BM);
+    kp.m_tiles = g.n_clips * kp.tiles_per_clip;
+    kp.n_tiles = g.N / g.group_size;
+    kp.n_stride = g.group_size;
+    kp.n_valid = g.group_size;
+    kp.num_kb = g.taps;
+    kp.clip_rows = g.clip_rows;
+    kp.clip_valid = g.clip_valid;
+    kp.pad_left = g.pad_left;
+  } else {
+    bn = (g.N % 256 == 0) ? 256 : (g.N % 128 == 0 ? 128 : 64);
+    if (g.N % bn != 0) return fail(kInvalidArgument, "gemm: N must be a multiple of 64");
+    kp.m_tiles = ceil_div(g.M, BM);
+    kp.n_tiles = g.N / bn;
+    kp.num_kb = g.K / BK;
+    kp.tiles_per_clip = 1;
+    kp.n_stride = bn;
+    kp.n_valid = bn;
+  }
+  if (kp.m_tiles <= 0 || kp.n_tiles <= 0 || kp.num_kb <= 0) return fail(kInvalidArgument, "gemm: empty problem");
+  switch (bn) {
+    case 256: return launch<256>(g, kp, stream);
+    case 128: return launch<128>(g, kp, stream);
+    default: return launch<64>(g, kp, stream);
+  }
+}
+
+}  // namespace svt

@@ -1,0 +1,49 @@
+// tcgen05 / TMEM / TMA GEMM used by every dense contraction on the hot path
+// (conv-as-GEMM, feature projection, QKV / out-proj / FFN, positional conv, fusion projections).
+#pragma once
+#include "common.cuh"
+
+namespace svt {
+
+enum GemmAct : int { kActNone = 0, kActGelu = 1, kActRelu = 2 };
+
+// C[row, n] = act( sum_k A[row, k] * W[n, k] + bias[n] ) (+ resid[row, n])
+//
+// A (bf16) is described as a 3-D TMA view so that the same kernel covers
+//   * plain row-major activations            dims (K, 1, M)
+//   * strided conv1d as implicit GEMM         dims (C_in, taps, M) with row stride = conv_stride * C_in
+//     (channel-last activations: the `taps` input rows of one output frame are contiguous in HBM, so
+//      im2col is nothing but an overlapping row stride -- no data is materialised)
+//   * the grouped positional conv             dims (D, T, B), one (clip, 128-frame) tile per CTA tile and
+//     one tap per k-block, the tap shift and the zero padding both done by TMA coordinates / OOB fill.
+// W (bf16, K-major, i.e. the nn.Linear layout [N, K]) is a 2-D TMA view.
+struct GemmArgs {
+  // ---- operands
+  const __nv_bfloat16* a = nullptr;
+  uint64_t a_dims[3] = {0, 1, 0};          // elements
+  uint64_t a_strides[2] = {0, 0};          // elements, for dims 1 and 2
+  const __nv_bfloat16* w = nullptr;        // [w_rows, K_w] row-major
+  int w_rows = 0;                          // total rows of the weight view
+  int w_cols = 0;                          // inner (K) extent of the weight view
+  // ---- problem
+  int mode = 0;                            // 0 linear, 1 positional conv
+  int M = 0;                               // linear: flat rows. posconv: unused
+  int N = 0;                               // output columns
+  int K = 0;                               // contraction length (posconv: taps * 64)
+  int k_inner = 0;                         // linear: a_dims[0]
+  // posconv geometry
+  int n_clips = 1, clip_rows = 0 /*T_alloc*/, clip_valid = 0 /*T*/, pad_left = 0, taps = 0;
+  int group_size = 64;                     // channels per group (weights zero-padded to 64 x 64 per tap)
+  // ---- epilogue
+  const float* bias = nullptr;             // [N] fp32 or null
+  const float* resid = nullptr;            // fp32 [rows, ld_resid] or null (may alias out_f32)
+  float* out_f32 = nullptr;
+  __nv_bfloat16* out_bf16 = nullptr;
+  int ld_out = 0;                          // leading dimension (elements) of out_f32 / out_bf16 / resid
+  int act = kActNone;
+  // optional second bf16 output written transposed per clip is not needed (attention reads row-major V)
+};
+
+int gemm_bf16_tc(const GemmArgs& g, cudaStream_t stream);
+
+}  // namespace svt

@@ -1,0 +1,115 @@
+// Host-side model objects behind the C ABI: weight registry (reference state_dict names),
+// packing into kernel layouts, workspace planning, forward orchestration.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/svt_b200.h"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "ops.cuh"
+
+namespace svt {
+
+struct RawTensor {
+  float* dev = nullptr;  // fp32 copy on the device
+  std::vector<int64_t> shape;
+  size_t numel() const {
+    size_t n = 1;
+    for (auto d : shape) n *= static_cast<size_t>(d);
+    return n;
+  }
+};
+
+// owns device allocations made while packing
+class DevicePool {
+ public:
+  ~DevicePool() { release(); }
+  int alloc(size_t bytes, void** out);
+  template <typename T>
+  int alloc_t(size_t n, T** out) { return alloc(n * sizeof(T), reinterpret_cast<void**>(out)); }
+  void release();
+
+ private:
+  std::vector<void*> ptrs_;
+};
+
+class WeightRegistry {
+ public:
+  ~WeightRegistry() { clear(); }
+  int set(const std::string& name, const float* host, const int64_t* shape, int ndim);
+  const RawTensor* find(const std::string& name) const;
+  int require(const std::string& name, std::initializer_list<int64_t> shape, const RawTensor** out) const;
+  void clear();
+
+ private:
+  std::map<std::string, RawTensor> t_;
+};
+
+struct LinearW {
+  __nv_bfloat16* w = nullptr;  // [N, K]
+  float* b = nullptr;          // [N]
+  int N = 0, K = 0;
+};
+struct NormW {
+  float* g = nullptr;
+  float* b = nullptr;
+};
+
+}  // namespace svt
+
+// ---------------------------------------------------------------------------------------------
+namespace svt {
+int pack_posconv_weight(const float* w_dev, const float* tap_scale, int D, int groups, int taps, __nv_bfloat16* dst,
+                        cudaStream_t stream);
+}
+
+struct svt_encoder {
+  ~svt_encoder() {
+    if (head_w != nullptr) cudaFree(head_w);
+    if (head_b != nullptr) cudaFree(head_b);
+  }
+  svt_encoder_config cfg{};
+  svt::WeightRegistry reg;
+  svt::DevicePool pool;
+  bool finalized = false;
+
+  // packed weights
+  float* conv0_w = nullptr;  // [k][C] fp32
+  float* conv0_b = nullptr;
+  svt::NormW conv0_norm;
+  std::vector<svt::LinearW> conv;   // layers 1..n-1: [C, k*C_in]
+  std::vector<svt::NormW> conv_norm;
+  svt::NormW proj_norm;
+  svt::LinearW proj;
+  __nv_bfloat16* pos_w = nullptr;  // [G][taps][64][64]
+  float* pos_b = nullptr;
+  svt::NormW enc_norm;
+  struct Layer {
+    svt::NormW ln1, ln2;
+    svt::LinearW qkv, out, ff1, ff2;
+  };
+  std::vector<Layer> layers;
+  float* head_w = nullptr;  // [n_out, D] fp32
+  float* head_b = nullptr;
+  int head_n = 0;
+
+  // geometry helpers
+  int conv_out_len(int L, int upto) const;  // valid frames after conv layers 0..upto
+  int t_alloc0(int L) const;                // allocated frames of layer 0 (multiple of prod(strides[1:]) and 4)
+};
+
+struct svt_fusion {
+  svt_fusion_config cfg{};
+  svt::WeightRegistry reg;
+  svt::DevicePool pool;
+  bool finalized = false;
+  struct Layer {
+    svt::LinearW qkv;   // [3D, D] (q rows pre-scaled by d_h^-0.5)
+    svt::LinearW out2;  // [D, 2D] = [alpha*Wo | (1-alpha)*Wo], bias bo
+    svt::NormW n1, n2;
+    svt::LinearW ff1, ff2;
+  };
+  Layer layer[2];
+};

@@ -1,0 +1,105 @@
+// Non-GEMM device ops of the hot path + their host launchers.
+#pragma once
+#include "common.cuh"
+
+namespace svt {
+
+// ---- attention (attention.cu)
+struct AttentionArgs {
+  const __nv_bfloat16* q = nullptr;  // row (clip*q_clip_rows + t), col head*head_dim + d
+  const __nv_bfloat16* k = nullptr;
+  const __nv_bfloat16* v = nullptr;
+  __nv_bfloat16* o = nullptr;
+  int ldq = 0, ldk = 0, ldv = 0, ldo = 0;
+  int Tq = 0, Tk = 0;                   // valid rows per clip
+  int q_clip_rows = 0, k_clip_rows = 0; // allocated rows per clip
+  int clips = 0, heads = 0, head_dim = 0;
+};
+int attention_bf16(const AttentionArgs& a, cudaStream_t stream);
+
+// ---- row ops (rowops.cu)
+// y = LayerNorm(x) over the last dim (biased variance), optional GELU afterwards.
+// x is fp32 or bf16 (exactly one non-null); writes bf16 and/or fp32.  D % 128 == 0, D <= 2048.
+struct LayerNormArgs {
+  const float* x_f32 = nullptr;
+  const __nv_bfloat16* x_bf16 = nullptr;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  __nv_bfloat16* y_bf16 = nullptr;
+  float* y_f32 = nullptr;
+  int rows = 0, D = 0;
+  float eps = 1e-5f;
+  int gelu = 0;
+  // optional: accumulate sum / sum-of-squares of the fp32 OUTPUT over rows with (row % clip_rows) < clip_valid
+  double* stats = nullptr;  // [2]
+  int clip_rows = 0, clip_valid = 0;
+};
+int layer_norm(const LayerNormArgs& a, cudaStream_t stream);
+
+// sum / sum of squares of an fp32 tensor (whole-tensor layer norm, huggingface_interface.py:289)
+int tensor_stats(const float* x, size_t n, double* stats /*[2], zeroed here*/, cudaStream_t stream);
+
+// conv layer 0 (C_in = 1): wav (B, L) fp32 -> (B, t_alloc, C) bf16 channel-last.
+//   layer mode : (x - mean) * rstd -> conv(k, s) + bias -> LN over C -> GELU          (large)
+//   group mode : (x - mean) * rstd -> conv(k, s) [+ bias], pre-norm bf16 + per-(clip, channel) sums (base)
+struct Conv0Args {
+  const float* wav = nullptr;
+  int B = 0, L = 0, T = 0, t_alloc = 0;
+  int C = 512, k = 10, stride = 5;
+  const float* w = nullptr;     // [k][C] fp32 (tap-major)
+  const float* bias = nullptr;  // [C] or null
+  const float* gamma = nullptr; // LN affine (layer mode)
+  const float* beta = nullptr;
+  const double* in_stats = nullptr;  // [2] sum, sumsq over the B*L input (null: no input normalisation)
+  __nv_bfloat16* out = nullptr;
+  int layer_mode = 1;
+  float* chan_stats = nullptr;  // group mode: [B][C][2] fp32 sums (zeroed by the launcher)
+};
+int conv0_forward(const Conv0Args& a, cudaStream_t stream);
+
+// group-norm apply (+GELU) for the base model's layer 0: in-place on (B, t_alloc, C) bf16
+int groupnorm_gelu_apply(__nv_bfloat16* x, const float* chan_stats, const float* gamma, const float* beta, int B, int T,
+                         int t_alloc, int C, cudaStream_t stream);
+
+// Output whole-tensor norm + head + frame post-processing:
+//   feats[b,t,:] = (x[b*clip_rows+t,:] - mean) * rstd    (mean/rstd from stats over valid rows; identity if !output_norm)
+//   logits[b,t,:] = feats . Wh^T + bh                     (n_out <= 32)
+struct HeadArgs {
+  const float* x = nullptr;  // [clips*clip_rows, D] fp32
+  int clips = 0, clip_rows = 0, T = 0, D = 0;
+  const double* stats = nullptr;  // [2] or null (no output norm)
+  float eps = 1e-5f;
+  const float* w = nullptr;  // [n_out, D] fp32 (null: no head)
+  const float* b = nullptr;
+  int n_out = 0;
+  float* feats = nullptr;   // [clips, T, D] compact, or null
+  float* logits = nullptr;  // [clips, T, n_out] compact, or null
+};
+int head_forward(const HeadArgs& a, cudaStream_t stream);
+
+// per-frame argmax over the octave / pitch-class logits (train_audio_ssl.py:95-99); first max wins
+int frame_argmax(const float* logits, int n_frames, int n_out, int oct_off, int n_oct, int pc_off, int n_pc, int32_t* oct,
+                 int32_t* pc, cudaStream_t stream);
+
+// ---- weight packing helpers (pack.cu): generic strided fp32 -> bf16/fp32 gather
+//   dst[i0][i1][i2][i3] (contiguous) = scale * src[i0*s0 + i1*s1 + i2*s2 + i3*s3] * (vec ? vec[i_vecdim] : 1)
+struct PackArgs {
+  const float* src = nullptr;
+  int dims[4] = {1, 1, 1, 1};
+  long long strides[4] = {0, 0, 0, 0};
+  float scale = 1.f;
+  const float* vec = nullptr;
+  int vec_dim = 0;
+};
+int pack_bf16(const PackArgs& a, __nv_bfloat16* dst, cudaStream_t stream);
+int pack_f32(const PackArgs& a, float* dst, cudaStream_t stream);
+// weight-norm(dim=2) factor g[j] / ||v[:,:,j]||  for the positional conv (HF modeling_wav2vec2.py:343-355)
+int weight_norm_scale(const float* v, const float* g, int d0, int d1, int taps, float* out, cudaStream_t stream);
+// x[b,t,:] += pe[t,:]  (sinusoidal table computed on the fly) -> bf16 + fp32 copies; zero rows t >= T_valid of src
+int add_positional_encoding(const float* x, int clips, int T_src, int T, int D, float* out_f32, __nv_bfloat16* out_bf16,
+                            cudaStream_t stream);
+// out = a + b (fp32, n elements)
+int add_f32(const float* a, const float* b, float* out, size_t n, cudaStream_t stream);
+int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, size_t n, cudaStream_t stream);
+
+}  // namespace svt

@@ -1,0 +1,517 @@
+// HBM-bound row kernels of the hot path: layer norms, the C_in=1 first conv layer (fused with the
+// whole-tensor input normalisation, LayerNorm and GELU), whole-tensor output norm + linear head,
+// frame post-processing.  All use 16-byte vectorised, warp-coalesced accesses and warp-shuffle reductions.
+#include "ops.cuh"
+
+namespace svt {
+
+namespace {
+
+__device__ __forceinline__ float4 ld_bf16x4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float a, float b, float c, float d) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+}
+
+__device__ __forceinline__ double block_sum_double(double v, double* sh) {
+  // warp reduce then 8-warp smem reduce (blockDim.x == 256)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+  __syncthreads();
+  return t;  // valid in thread 0
+}
+
+// ------------------------------------------------------------------------------------ LayerNorm
+// one warp per row, NV float4 groups per lane (D = NV * 128)
+template <int NV>
+__global__ void __launch_bounds__(256)
+layer_norm_kernel(const float* __restrict__ xf, const __nv_bfloat16* __restrict__ xb, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, __nv_bfloat16* __restrict__ yb, float* __restrict__ yf, int rows,
+                  float eps, int gelu, double* __restrict__ stats, int clip_rows, int clip_valid) {
+  constexpr int D = NV * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  float s_out = 0.f, ss_out = 0.f;
+  if (row < rows) {
+    float4 v[NV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const size_t off = static_cast<size_t>(row) * D + (i * 32 + lane) * 4;
+      v[i] = (xf != nullptr) ? *reinterpret_cast<const float4*>(xf + off) : ld_bf16x4(xb + off);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(sum) * (1.0f / D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 y;
+      y.x = v[i].x * rstd * g.x + b.x;
+      y.y = v[i].y * rstd * g.y + b.y;
+      y.z = v[i].z * rstd * g.z + b.z;
+      y.w = v[i].w * rstd * g.w + b.w;
+      if (gelu) { y.x = gelu_erf(y.x); y.y = gelu_erf(y.y); y.z = gelu_erf(y.z); y.w = gelu_erf(y.w); }
+      const size_t off = static_cast<size_t>(row) * D + c;
+      if (yb != nullptr) st_bf16x4(yb + off, y.x, y.y, y.z, y.w);
+      if (yf != nullptr) *reinterpret_cast<float4*>(yf + off) = y;
+      s_out += (y.x + y.y) + (y.z + y.w);
+      ss_out += (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);
+    }
+    if (stats != nullptr && (row % clip_rows) >= clip_valid) { s_out = 0.f; ss_out = 0.f; }
+  }
+  if (stats != nullptr) {
+    __shared__ double sh[8];
+    const double a = block_sum_double(static_cast<double>(s_out), sh);
+    const double b = block_sum_double(static_cast<double>(ss_out), sh);
+    if (threadIdx.x == 0) { atomicAdd(stats, a); atomicAdd(stats + 1, b); }
+  }
+}
+
+// ------------------------------------------------------------------------------------ tensor stats
+__global__ void __launch_bounds__(256) tensor_stats_kernel(const float* __restrict__ x, size_t n, double* stats) {
+  float s = 0.f, ss = 0.f;
+  const size_t n4 = n / 4;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    s += (v.x + v.y) + (v.z + v.w);
+    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float v = x[n4 * 4 + threadIdx.x];
+    s += v; ss += v * v;
+  }
+  __shared__ double sh[8];
+  const double a = block_sum_double(static_cast<double>(s), sh);
+  const double b = block_sum_double(static_cast<double>(ss), sh);
+  if (threadIdx.x == 0) { atomicAdd(stats, a); atomicAdd(stats + 1, b); }
+}
+
+__device__ __forceinline__ void mean_rstd_from_stats(const double* stats, double n, float eps, float& mean, float& rstd) {
+  const double m = stats[0] / n;
+  double var = stats[1] / n - m * m;
+  if (var < 0.0) var = 0.0;
+  mean = static_cast<float>(m);
+  rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+// ------------------------------------------------------------------------------------ conv layer 0
+// C = 512, k = 10, stride = 5.  One warp computes 4 consecutive frames; lane owns channels
+// {i*128 + lane*4 + e : i<4, e<4}.  Weights [k][C] fp32 live in shared memory.
+constexpr int kC0 = 512, kK0 = 10, kS0 = 5, kR0 = 4;
+constexpr int kConv0GroupsPerWarp = 5;
+
+template <bool kLayerMode>
+__global__ void __launch_bounds__(256)
+conv0_kernel(const float* __restrict__ wav, int L, int T, int t_alloc, const float* __restrict__ w,
+             const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+             const double* __restrict__ in_stats, double n_in, __nv_bfloat16* __restrict__ out,
+             float* __restrict__ chan_stats) {
+  __shared__ __align__(16) float sw[kK0 * kC0];
+  __shared__ __align__(16) float sbias[kC0];
+  __shared__ __align__(16) float sgamma[kC0];
+  __shared__ __align__(16) float sbeta[kC0];
+  for (int i = threadIdx.x; i < kK0 * kC0; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < kC0; i += blockDim.x) {
+    sbias[i] = bias != nullptr ? bias[i] : 0.f;
+    sgamma[i] = kLayerMode ? gamma[i] : 1.f;
+    sbeta[i] = kLayerMode ? beta[i] : 0.f;
+  }
+  __syncthreads();
+  float mean = 0.f, rstd = 1.f;
+  if (in_stats != nullptr) mean_rstd_from_stats(in_stats, n_in, 1e-5f, mean, rstd);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int clip = blockIdx.y;
+  const float* x = wav + static_cast<size_t>(clip) * L;
+  __nv_bfloat16* o = out + static_cast<size_t>(clip) * t_alloc * kC0;
+  float cs[16], css[16];  // group mode: per-channel sums over this warp's frames
+#pragma unroll
+  for (int i = 0; i < 16; ++i) cs[i] = css[i] = 0.f;
+
+  for (int gi = 0; gi < kConv0GroupsPerWarp; ++gi) {
+    const int t0 = ((blockIdx.x * 8 + warp) * kConv0GroupsPerWarp + gi) * kR0;
+    if (t0 >= t_alloc) break;
+    // 25 input samples cover 4 frames; lane l holds sample 5*t0 + l
+    const int si = kS0 * t0 + lane;
+    float xv = (lane < kS0 * (kR0 - 1) + kK0 && si < L) ? (__ldg(x + si) - mean) * rstd : 0.f;
+    float acc[kR0][16];
+#pragma unroll
+    for (int r = 0; r < kR0; ++r)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[r][i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kK0; ++j) {
+      float4 wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) wv[i] = *reinterpret_cast<const float4*>(&sw[j * kC0 + i * 128 + lane * 4]);
+#pragma unroll
+      for (int r = 0; r < kR0; ++r) {
+        const float xs = __shfl_sync(0xffffffffu, xv, kS0 * r + j);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[r][4 * i + 0] = fmaf(xs, wv[i].x, acc[r][4 * i + 0]);
+          acc[r][4 * i + 1] = fmaf(xs, wv[i].y, acc[r][4 * i + 1]);
+          acc[r][4 * i + 2] = fmaf(xs, wv[i].z, acc[r][4 * i + 2]);
+          acc[r][4 * i + 3] = fmaf(xs, wv[i].w, acc[r][4 * i + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kR0; ++r) {
+      const int t = t0 + r;
+      __nv_bfloat16* orow = o + static_cast<size_t>(t) * kC0;
+      if (t >= T) {  // allocation padding rows: keep finite
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st_bf16x4(orow + i * 128 + lane * 4, 0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 b = *reinterpret_cast<const float4*>(&sbias[i * 128 + lane * 4]);
+        acc[r][4 * i + 0] += b.x; acc[r][4 * i + 1] += b.y; acc[r][4 * i + 2] += b.z; acc[r][4 * i + 3] += b.w;
+        sum += (acc[r][4 * i] + acc[r][4 * i + 1]) + (acc[r][4 * i + 2] + acc[r][4 * i + 3]);
+      }
+      if (kLayerMode) {
+        const float mu = warp_sum(sum) * (1.0f / kC0);
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { acc[r][i] -= mu; sq = fmaf(acc[r][i], acc[r][i], sq); }
+        const float rs = rsqrtf(warp_sum(sq) * (1.0f / kC0) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 g = *reinterpret_cast<const float4*>(&sgamma[i * 128 + lane * 4]);
+          const float4 b = *reinterpret_cast<const float4*>(&sbeta[i * 128 + lane * 4]);
+          st_bf16x4(orow + i * 128 + lane * 4, gelu_erf(acc[r][4 * i + 0] * rs * g.x + b.x),
+                    gelu_erf(acc[r][4 * i + 1] * rs * g.y + b.y), gelu_erf(acc[r][4 * i + 2] * rs * g.z + b.z),
+                    gelu_erf(acc[r][4 * i + 3] * rs * g.w + b.w));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { cs[i] += acc[r][i]; css[i] = fmaf(acc[r][i], acc[r][i], css[i]); }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          st_bf16x4(orow + i * 128 + lane * 4, acc[r][4 * i], acc[r][4 * i + 1], acc[r][4 * i + 2], acc[r][4 * i + 3]);
+      }
+    }
+  }
+  if (!kLayerMode) {
+    float* st = chan_stats + static_cast<size_t>(clip) * kC0 * 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = i * 128 + lane * 4 + e;
+        atomicAdd(st + 2 * c, cs[4 * i + e]);
+        atomicAdd(st + 2 * c + 1, css[4 * i + e]);
+      }
+  }
+}
+
+// group-norm apply + GELU, in place.  block = 256 threads = 4 frames x 64 channel-octets
+__global__ void __launch_bounds__(256)
+groupnorm_gelu_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ chan_stats,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, int T, int t_alloc, int C,
+                      int frames_per_block) {
+  const int clip = blockIdx.y;
+  const int c0 = (threadIdx.x & 63) * 8;
+  const int sub = threadIdx.x >> 6;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float* st = chan_stats + (static_cast<size_t>(clip) * C + c0 + e) * 2;
+    const float m = st[0] / T;
+    const float var = fmaxf(st[1] / T - m * m, 0.f);
+    const float rs = rsqrtf(var + 1e-5f);
+    sc[e] = rs * gamma[c0 + e];
+    sh[e] = beta[c0 + e] - m * sc[e];
+  }
+  const int tbeg = blockIdx.x * frames_per_block;
+  for (int t = tbeg + sub; t < tbeg + frames_per_block && t < T; t += 4) {
+    __nv_bfloat16* p = x + (static_cast<size_t>(clip) * t_alloc + t) * C + c0;
+    const float4 a = ld_bf16x4(p), b = ld_bf16x4(p + 4);
+    st_bf16x4(p, gelu_erf(a.x * sc[0] + sh[0]), gelu_erf(a.y * sc[1] + sh[1]), gelu_erf(a.z * sc[2] + sh[2]),
+              gelu_erf(a.w * sc[3] + sh[3]));
+    st_bf16x4(p + 4, gelu_erf(b.x * sc[4] + sh[4]), gelu_erf(b.y * sc[5] + sh[5]), gelu_erf(b.z * sc[6] + sh[6]),
+              gelu_erf(b.w * sc[7] + sh[7]));
+  }
+}
+
+// ------------------------------------------------------------------------------------ output norm + head
+template <int NV>
+__global__ void __launch_bounds__(256)
+head_kernel(const float* __restrict__ x, int clips, int clip_rows, int T, const double* __restrict__ stats, float eps,
+            const float* __restrict__ w, const float* __restrict__ b, int n_out, float* __restrict__ feats,
+            float* __restrict__ logits, int w_in_smem) {
+  constexpr int D = NV * 128;
+  extern __shared__ __align__(16) float sw[];
+  if (w != nullptr && w_in_smem)
+    for (int i = threadIdx.x; i < n_out * D; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  float mean = 0.f, rstd = 1.f;
+  if (stats != nullptr) mean_rstd_from_stats(stats, static_cast<double>(clips) * T * D, eps, mean, rstd);
+  const float* wp = w_in_smem ? sw : w;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = clips * T;
+  for (int fr = blockIdx.x * 8 + warp; fr < total; fr += gridDim.x * 8) {
+    const int clip = fr / T, t = fr % T;
+    const float* xr = x + (static_cast<size_t>(clip) * clip_rows + t) * D;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+      v[i].x = (v[i].x - mean) * rstd; v[i].y = (v[i].y - mean) * rstd;
+      v[i].z = (v[i].z - mean) * rstd; v[i].w = (v[i].w - mean) * rstd;
+      if (feats != nullptr) *reinterpret_cast<float4*>(feats + static_cast<size_t>(fr) * D + (i * 32 + lane) * 4) = v[i];
+    }
+    if (logits != nullptr) {
+      float mine = 0.f;
+      for (int n = 0; n < n_out; ++n) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const float4 ww = *reinterpret_cast<const float4*>(wp + static_cast<size_t>(n) * D + (i * 32 + lane) * 4);
+          acc = fmaf(v[i].x, ww.x, acc); acc = fmaf(v[i].y, ww.y, acc);
+          acc = fmaf(v[i].z, ww.z, acc); acc = fmaf(v[i].w, ww.w, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == n) mine = acc + (b != nullptr ? b[n] : 0.f);
+      }
+      if (lane < n_out) logits[static_cast<size_t>(fr) * n_out + lane] = mine;
+    }
+  }
+}
+
+__global__ void frame_argmax_kernel(const float* __restrict__ logits, int n_frames, int n_out, int oct_off, int n_oct,
+                                    int pc_off, int n_pc, int32_t* __restrict__ oct, int32_t* __restrict__ pc) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  const float* r = logits + static_cast<size_t>(f) * n_out;
+  int bo = 0, bp = 0;
+  float vo = r[oct_off], vp = r[pc_off];
+  for (int i = 1; i < n_oct; ++i) if (r[oct_off + i] > vo) { vo = r[oct_off + i]; bo = i; }  // first max wins
+  for (int i = 1; i < n_pc; ++i) if (r[pc_off + i] > vp) { vp = r[pc_off + i]; bp = i; }
+  oct[f] = bo;
+  pc[f] = bp;
+}
+
+// ------------------------------------------------------------------------------------ misc
+__global__ void add_pe_kernel(const float* __restrict__ x, int T_src, int T, int D, float* __restrict__ of,
+                              __nv_bfloat16* __restrict__ ob) {
+  // x: [clips, T_src, D]; out: [clips, T, D]; rows t >= T_src are zero before adding the encoding (fusion.py:198-203)
+  const int clip = blockIdx.y, t = blockIdx.x;
+  const float kNegLog = -(logf(10000.0f) / static_cast<float>(D));
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float denom = expf(static_cast<float>(c & ~1) * kNegLog);
+    const float ang = static_cast<float>(t) * denom;
+    const float pe = (c & 1) ? cosf(ang) : sinf(ang);
+    const float v = (t < T_src ? x[(static_cast<size_t>(clip) * T_src + t) * D + c] : 0.f) + pe;
+    const size_t o = (static_cast<size_t>(clip) * T + t) * D + c;
+    if (of != nullptr) of[o] = v;
+    if (ob != nullptr) ob[o] = __float2bfloat16(v);
+  }
+}
+
+__global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) o[i] = a[i] + b[i];
+}
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = __float2bfloat16(x[i]);
+}
+
+template <typename OutT>
+__global__ void pack_kernel(const float* __restrict__ src, int d0, int d1, int d2, int d3, long long s0, long long s1,
+                            long long s2, long long s3, float scale, const float* __restrict__ vec, int vec_dim,
+                            OutT* __restrict__ dst) {
+  const size_t n = static_cast<size_t>(d0) * d1 * d2 * d3;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    size_t r = i;
+    const int i3 = r % d3; r /= d3;
+    const int i2 = r % d2; r /= d2;
+    const int i1 = r % d1; r /= d1;
+    const int i0 = static_cast<int>(r);
+    float v = src[i0 * s0 + i1 * s1 + i2 * s2 + i3 * s3] * scale;
+    if (vec != nullptr) v *= vec[vec_dim == 0 ? i0 : (vec_dim == 1 ? i1 : (vec_dim == 2 ? i2 : i3))];
+    if constexpr (sizeof(OutT) == 2) dst[i] = __float2bfloat16(v); else dst[i] = v;
+  }
+}
+
+__global__ void weight_norm_scale_kernel(const float* __restrict__ v, const float* __restrict__ g, int n01, int taps,
+                                         float* __restrict__ out) {
+  const int j = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n01; i += blockDim.x) {
+    const double x = v[static_cast<size_t>(i) * taps + j];
+    s += x * x;
+  }
+  __shared__ double sh[8];
+  const double tot = block_sum_double(s, sh);
+  if (threadIdx.x == 0) out[j] = static_cast<float>(static_cast<double>(g[j]) / sqrt(tot));
+}
+
+template <typename F>
+int dispatch_nv(int D, F&& f) {
+  switch (D / 128) {
+    case 2: return f(std::integral_constant<int, 2>{});
+    case 4: return f(std::integral_constant<int, 4>{});
+    case 6: return f(std::integral_constant<int, 6>{});
+    case 8: return f(std::integral_constant<int, 8>{});
+    case 16: return f(std::integral_constant<int, 16>{});
+    default: return fail(kUnsupported, "row op: D must be one of 256/512/768/1024/2048, got " + std::to_string(D));
+  }
+}
+
+}  // namespace
+
+int layer_norm(const LayerNormArgs& a, cudaStream_t stream) {
+  if (a.rows <= 0) return kOk;
+  if (a.D % 128 != 0) return fail(kUnsupported, "layer_norm: D % 128 != 0");
+  if ((a.x_f32 == nullptr) == (a.x_bf16 == nullptr)) return fail(kInvalidArgument, "layer_norm: exactly one input");
+  const int clip_rows = a.clip_rows > 0 ? a.clip_rows : 1;
+  const int clip_valid = a.clip_rows > 0 ? a.clip_valid : 1;
+  return dispatch_nv(a.D, [&](auto nv) {
+    layer_norm_kernel<decltype(nv)::value><<<ceil_div(a.rows, 8), 256, 0, stream>>>(
+        a.x_f32, a.x_bf16, a.gamma, a.beta, a.y_bf16, a.y_f32, a.rows, a.eps, a.gelu, a.stats, clip_rows, clip_valid);
+    SVT_CUDA(cudaGetLastError());
+    return static_cast<int>(kOk);
+  });
+}
+
+int tensor_stats(const float* x, size_t n, double* stats, cudaStream_t stream) {
+  SVT_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(double), stream));
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return fail(kInvalidArgument, "tensor_stats: input must be 16-byte aligned");
+  const int grid = num_sms() * 4;
+  tensor_stats_kernel<<<grid, 256, 0, stream>>>(x, n, stats);
+  SVT_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int conv0_forward(const Conv0Args& a, cudaStream_t stream) {
+  if (a.C != kC0 || a.k != kK0 || a.stride != kS0)
+    return fail(kUnsupported, "conv0: only C=512, kernel=10, stride=5 (every wav2vec2/HuBERT checkpoint) is built");
+  if (a.t_alloc % kR0 != 0) return fail(kInvalidArgument, "conv0: t_alloc % 4 != 0");
+  const int groups = a.t_alloc / kR0;
+  dim3 grid(ceil_div(groups, 8 * kConv0GroupsPerWarp), a.B);
+  const double n_in = static_cast<double>(a.B) * a.L;
+  if (a.layer_mode) {
+    conv0_kernel<true><<<grid, 256, 0, stream>>>(a.wav, a.L, a.T, a.t_alloc, a.w, a.bias, a.gamma, a.beta, a.in_stats,
+                                                 n_in, a.out, nullptr);
+  } else {
+    SVT_CUDA(cudaMemsetAsync(a.chan_stats, 0, sizeof(float) * 2 * a.C * a.B, stream));
+    conv0_kernel<false><<<grid, 256, 0, stream>>>(a.wav, a.L, a.T, a.t_alloc, a.w, a.bias, nullptr, nullptr, a.in_stats,
+                                                  n_in, a.out, a.chan_stats);
+  }
+  SVT_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int groupnorm_gelu_apply(__nv_bfloat16* x, const float* chan_stats, const float* gamma, const float* beta, int B, int T,
+                         int t_alloc, int C, cudaStream_t stream) {
+  if (C != 512) return fail(kUnsupported, "groupnorm: C must be 512");
+  const int fpb = 64;
+  dim3 grid(ceil_div(T, fpb), B);
+  groupnorm_gelu_kernel<<<grid, 256, 0, stream>>>(x, chan_stats, gamma, beta, T, t_alloc, C, fpb);
+  SVT_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int head_forward(const HeadArgs& a, cudaStream_t stream) {
+  if (a.n_out > 32) return fail(kUnsupported, "head: n_out must be <= 32");
+  if (a.clips * a.T <= 0) return kOk;
+  return dispatch_nv(a.D, [&](auto nv) {
+    constexpr int NV = decltype(nv)::value;
+    size_t smem = (a.w != nullptr) ? sizeof(float) * a.n_out * a.D : 0;
+    int w_in_smem = 1;
+    if (smem > 160 * 1024) { smem = 0; w_in_smem = 0; }
+    static bool attr_set = false;
+    if (!attr_set) {
+      SVT_CUDA(cudaFuncSetAttribute(head_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_set = true;
+    }
+    int grid = ceil_div(a.clips * a.T, 8);
+    if (grid > num_sms()) grid = num_sms();
+    head_kernel<NV><<<grid, 256, smem, stream>>>(a.x, a.clips, a.clip_rows, a.T, a.stats, a.eps, a.w, a.b, a.n_out,
+                                                 a.feats, a.logits, w_in_smem);
+    SVT_CUDA(cudaGetLastError());
+    return static_cast<int>(kOk);
+  });
+}
+
+int frame_argmax(const float* logits, int n_frames, int n_out, int oct_off, int n_oct, int pc_off, int n_pc, int32_t* oct,
+                 int32_t* pc, cudaStream_t stream) {
+  if (n_frames <= 0) return kOk;
+  frame_argmax_kernel<<<ceil_div(n_frames, 256), 256, 0, stream>>>(logits, n_frames, n_out, oct_off, n_oct, pc_off, n_pc,
+                                                                  oct, pc);
+  SVT_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int pack_bf16(const PackArgs& a, __nv_bfloat16* dst, cudaStream_t stream) {
+  const size_t n = static_cast<size_t>(a.dims[0]) * a.dims[1] * a.dims[2] * a.dims[3];
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, 4096));
+  pack_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a.src, a.dims[0], a.dims[1], a.dims[2], a.dims[3], a.strides[0],
+                                                      a.strides[1], a.strides[2], a.strides[3], a.scale, a.vec,
+                                                      a.vec_dim, dst);
+  SVT_CUDA(cudaGetLastError());
+  return kOk;
+}
+int pack_f32(const PackArgs& a, float* dst, cudaStream_t stream) {
+  const size_t n = static_cast<size_t>(a.dims[0]) * a.dims[1] * a.dims[2] * a.dims[3];
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, 4096));
+  pack_kernel<float><<<grid, 256, 0, stream>>>(a.src, a.dims[0], a.dims[1], a.dims[2], a.dims[3], a.strides[0],
+                                              a.strides[1], a.strides[2], a.strides[3], a.scale, a.vec, a.vec_dim, dst);
+  SVT_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int weight_norm_scale(const float* v, const float* g, int d0, int d1, int taps, float* out, cudaStream_t stream) {
+  weight_norm_scale_kernel<<<taps, 256, 0, stream>>>(v, g, d0 * d1, taps, out);
+  SVT_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int add_positional_encoding(const float* x, int clips, int T_src, int T, int D, float* out_f32, __nv_bfloat16* out_bf16,
+                            cudaStream_t stream) {
+  dim3 grid(T, clips);
+  add_pe_kernel<<<grid, 256, 0, stream>>>(x, T_src, T, D, out_f32, out_bf16);
+  SVT_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int add_f32(const float* a, const float* b, float* out, size_t n, cudaStream_t stream) {
+  add_f32_kernel<<<num_sms() * 4, 256, 0, stream>>>(a, b, out, n);
+  SVT_CUDA(cudaGetLastError());
+  return kOk;
+}
+int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, size_t n, cudaStream_t stream) {
+  cast_bf16_kernel<<<num_sms() * 4, 256, 0, stream>>>(x, y, n);
+  SVT_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace svt

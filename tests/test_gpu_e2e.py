@@ -1,0 +1,191 @@
+"""End-to-end parity of the CUDA path (through the reference-shaped modules and the C ABI) against the CPU
+oracle and the committed golden vectors produced by the real reference.
+
+Tolerances (stated here as the north star asks): the kernels store activations in bf16 and accumulate in fp32,
+the oracle/reference are fp32 throughout.  Frame logits: rel-L2 <= 2e-2 and max-abs <= 0.1 (logits are O(1)
+after the whole-tensor output norm).  Decoded notes: bit-exact given identical logits."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+LOGIT_REL_L2 = 2e-2
+LOGIT_MAX_ABS = 0.1
+
+
+def _build(cfg, seed_sd=None):
+    """Reference-shaped modules with the seeded weights of the golden fixtures."""
+    import tempfile
+
+    from transformers import Wav2Vec2Config, Wav2Vec2FeatureExtractor, Wav2Vec2Model
+
+    import svt_speechbrain_b200 as svt
+    from oracle import make_golden as mg
+    from oracle import wav2vec2_oracle as wo
+
+    sd = mg.perturb_norm_affines(wo.random_weights(cfg, seed=0), seed=7) if seed_sd is None else seed_sd
+    head = wo.random_head(cfg.hidden_size, 20, seed=0)
+    d = os.path.join(tempfile.mkdtemp(), "wav2vec2-test")
+    os.makedirs(d)
+    Wav2Vec2Config(**cfg.hf_kwargs()).save_pretrained(d)
+    Wav2Vec2FeatureExtractor(feature_size=1, sampling_rate=16000, padding_value=0.0, do_normalize=True,
+                             return_attention_mask=True).save_pretrained(d)
+    lobe = svt.HuggingFaceWav2Vec2(source=d, save_path=d, pretrain=False, output_norm=True, freeze=True)
+    missing = lobe.load_state_dict(sd, strict=True)
+    lin = svt.Linear(n_neurons=20, input_size=cfg.hidden_size)
+    lin.load_state_dict(head)
+    return lobe.cuda(), lin.cuda(), sd, head
+
+
+def _check_logits(got, ref, tag):
+    got = got.detach().float().cpu().numpy()
+    err = np.abs(got - ref).max()
+    rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    print(f"{tag}: logits max-abs {err:.4e} rel-L2 {rel:.4e}")
+    assert np.isfinite(got).all()
+    assert rel <= LOGIT_REL_L2 and err <= LOGIT_MAX_ABS, (tag, err, rel)
+
+
+@pytest.mark.parametrize("name", ["w2v2_large_1s", "w2v2_base_1s", "w2v2_large_5s"])
+def test_encoder_vs_reference_golden(name):
+    from oracle import make_golden as mg
+    from oracle import wav2vec2_oracle as wo
+    import svt_speechbrain_b200 as svt
+
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    cfg = wo.W2V2Config.base() if "base" in name else wo.W2V2Config.large()
+    lobe, lin, sd, head = _build(cfg)
+    wav = mg.synth_wav(int(g["B"]), int(g["L"]), seed=int(g["wav_seed"])).cuda()
+    # (1) module-by-module, exactly like AMT.compute_forward: feats = lobe(wav); logits = head(feats)
+    feats = lobe(wav)
+    assert feats.shape == (int(g["B"]), cfg.num_frames(int(g["L"])), cfg.hidden_size) and feats.dtype == torch.float32
+    logits = lin(feats)
+    _check_logits(logits, g["logits"], name + " lobe->Linear")
+    fh = feats[:, :, :8].cpu().numpy()
+    assert np.abs(fh - g["feats_head"]).max() < 0.15
+    # (2) fused encoder+head entry point
+    tr = svt.AMTTranscriber(lobe, lin)
+    lg2 = tr.logits(wav)
+    _check_logits(lg2, g["logits"], name + " fused")
+    assert torch.allclose(lg2, logits, atol=1e-4)
+
+
+def test_encoder_vs_oracle_odd_length_and_batch_coupling():
+    """A length that is not a multiple of anything, B=3: the whole-tensor norms couple the clips of a call."""
+    from oracle import make_golden as mg
+    from oracle import wav2vec2_oracle as wo
+
+    cfg = wo.W2V2Config.large()
+    lobe, lin, sd, head = _build(cfg)
+    wav = mg.synth_wav(3, 16123, seed=5)
+    wav[1] *= 3.0  # make clips statistically different so per-clip vs whole-batch norms differ
+    with torch.no_grad():
+        ref = wo.amt_logits(cfg, sd, head, wav).numpy()
+        ref_single = wo.amt_logits(cfg, sd, head, wav[1:2]).numpy()
+    got = lin(lobe(wav.cuda()))
+    _check_logits(got, ref, "large odd-length B=3")
+    got_single = lin(lobe(wav[1:2].cuda()))
+    _check_logits(got_single, ref_single, "large odd-length B=1")
+    assert np.abs(ref[1] - ref_single[0]).max() > 1e-2  # the coupling is real, and we reproduce both
+
+
+def test_state_dict_keys_match_reference_layout():
+    from oracle import wav2vec2_oracle as wo
+
+    cfg = wo.W2V2Config.large()
+    lobe, lin, sd, head = _build(cfg)
+    assert set(lobe.state_dict().keys()) == set(sd.keys())
+    assert set(lin.state_dict().keys()) == {"w.weight", "w.bias"}
+
+
+@pytest.mark.parametrize("name", ["fusion_full", "fusion_full_pad"])
+def test_fusion_vs_reference_golden(name):
+    import svt_speechbrain_b200 as svt
+    from oracle import make_golden as mg
+
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    D = int(g["D"])
+    sd = mg.random_fusion_weights(D, int(g["d_ffn"]), seed=int(g["w_seed"]))
+    fus = svt.FusionRCA(alpha=0.5, nhead=int(g["nhead"]), d_ffn=int(g["d_ffn"]), d_model=D)
+    full = dict(fus.state_dict())
+    assert set(sd.keys()) | {"fusion.positional_encoding.pe"} == set(full.keys())
+    full.update(sd)
+    fus.load_state_dict(full, strict=True)
+    fus = fus.cuda()
+    gen = torch.Generator().manual_seed(int(g["x_seed"]))
+    a = torch.randn(int(g["B"]), int(g["Ta"]), D, generator=gen)
+    v = torch.randn(int(g["B"]), int(g["Tv"]), D, generator=gen)
+    out = fus(a.cuda(), v.cuda()).cpu().numpy()
+    ref = g["out"]
+    err = np.abs(out - ref).max()
+    rel = np.linalg.norm(out - ref) / np.linalg.norm(ref)
+    print(f"{name}: max-abs {err:.4e} rel-L2 {rel:.4e}")
+    # outputs are sums of two LayerNorm outputs (O(1)); bf16 storage inside -> same tolerance as the logits
+    assert rel <= 2e-2 and err <= 0.15
+
+
+def test_notes_bit_exact_from_identical_logits():
+    """Decoder parity is defined on identical logits: device argmax + host sigmoid + C decoder
+    == oracle frame_info + Python restatement of frame2note, bit for bit."""
+    import svt_speechbrain_b200 as svt
+    from oracle import wav2vec2_oracle as wo
+    from oracle.frame2note_oracle import frame2note as f2n_oracle
+
+    rng = np.random.default_rng(3)
+    n = 4000
+    lg = rng.normal(0, 2.0, (n, 20)).astype(np.float32)
+    lg[1:, 0][rng.random(n - 1) < 0.2] = lg[:-1, 0][rng.random(n - 1) < 0.2].mean()  # plateaus
+    lg[:, 2:7] = np.round(lg[:, 2:7])  # argmax ties
+    logits = torch.from_numpy(lg)
+    p_on, p_off, octv, pc = wo.frame_info_from_logits(logits)
+    fi = [(p_on[i], p_off[i], int(octv[i]), int(pc[i])) for i in range(n)]
+    want = np.array(f2n_oracle(fi, 0.4, 0.5, 1 / 49.8), dtype=np.float64).reshape(-1, 3)
+
+    class _Head:  # minimal stand-in: decode() only needs hparams
+        pass
+    tr = svt.AMTTranscriber.__new__(svt.AMTTranscriber)
+    tr.hp = svt.AMTHparams()
+    got = tr.decode(logits.cuda())
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert len(want) > 50
+
+
+def test_transcribe_song_matches_oracle_pipeline():
+    """30 s synthetic 'song' -> 5-s utterances (reference chunk rule) -> notes.  The oracle runs the same chunks
+    on the CPU; note lists are compared, frame logits within tolerance.  (Random-init logits have small margins,
+    so exact note equality under bf16 is reported, not asserted -- SURVEY.md 7 'hard parts'.)"""
+    import svt_speechbrain_b200 as svt
+    from oracle import make_golden as mg
+    from oracle import wav2vec2_oracle as wo
+    from oracle.frame2note_oracle import frame2note as f2n_oracle
+
+    cfg = wo.W2V2Config.base()
+    lobe, lin, sd, head = _build(cfg)
+    hp = svt.AMTHparams()
+    song = mg.synth_wav(1, 16000 * 12 + 1234, seed=9)[0]
+    spans = svt.split_song(song.numel(), hp)
+    assert spans[0] == (0, 80000) and spans[-1][1] == song.numel() and len(spans) == 2
+    tr = svt.AMTTranscriber(lobe, lin, hp)
+    with torch.no_grad():
+        ref_logits = torch.cat([wo.amt_logits(cfg, sd, head, song[a:b][None])[0] for a, b in spans])
+    got_logits = torch.cat([tr.logits(song[a:b][None].cuda())[0] for a, b in spans])
+    _check_logits(got_logits, ref_logits.numpy(), "song logits")
+    notes = tr.transcribe_song(song)
+    # decoding OUR logits with the oracle decoder must give exactly our notes
+    p_on, p_off, octv, pc = wo.frame_info_from_logits(got_logits.cpu())
+    fi = [(p_on[i], p_off[i], int(octv[i]), int(pc[i])) for i in range(len(p_on))]
+    want = np.array(f2n_oracle(fi, hp.onset_threshold, hp.offset_threshold, 1 / hp.frame_rate), dtype=np.float64).reshape(-1, 3)
+    assert notes.shape == want.shape and np.array_equal(notes, want)
+
+
+def test_cpu_tensor_is_rejected_loudly():
+    from oracle import wav2vec2_oracle as wo
+
+    cfg = wo.W2V2Config.base()
+    lobe, lin, _, _ = _build(cfg)
+    with pytest.raises(RuntimeError):
+        lobe(torch.randn(1, 16000))

@@ -43,6 +43,8 @@ int svt_version(void);
 const char* svt_last_error(void);
 /* number of CUDA devices visible (0 on a CPU-only box); never fails */
 int svt_device_count(void);
+/* kernels launched by this library since it was loaded (all streams); used by bench.py's gpu_launches */
+long long svt_debug_launch_count(void);
 
 /* ------------------------------------------------------------------ wav2vec2-style SSL encoder + head */
 typedef struct svt_encoder svt_encoder;

@@ -1,4 +1,5 @@
 // C-ABI glue: error state, device probing, kernel-level hooks.
+#include <atomic>
 #include <mutex>
 
 #include "model.cuh"
@@ -11,6 +12,9 @@ int fail(int code, const std::string& msg) {
   g_last_error = msg;
   return code;
 }
+static std::atomic<long long> g_launches{0};
+void note_kernel_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(); }
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -29,6 +33,7 @@ using namespace svt;
 extern "C" {
 
 int svt_version(void) { return 100; }
+long long svt_debug_launch_count(void) { return launch_count(); }
 const char* svt_last_error(void) { return g_last_error.c_str(); }
 int svt_device_count(void) {
   int n = 0;

@@ -236,7 +236,7 @@ int launch_attention(const AttentionArgs& a, cudaStream_t stream) {
   dim3 grid(ceil_div(a.Tq, kBQ), a.heads, a.clips);
   attention_kernel<DH><<<grid, kAttnThreads, smem, stream>>>(a.q, a.k, a.v, a.o, a.ldq, a.ldk, a.ldv, a.ldo, a.Tq, a.Tk,
                                                              a.q_clip_rows, a.k_clip_rows);
-  SVT_CUDA(cudaGetLastError());
+  SVT_POST_LAUNCH();
   return kOk;
 }
 

@@ -33,6 +33,13 @@ int fail(int code, const std::string& msg);
       return ::svt::fail(::svt::kCudaError, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
+// after every kernel launch: count it (svt_debug_launch_count) and surface launch errors
+#define SVT_POST_LAUNCH()             \
+  do {                                \
+    ::svt::note_kernel_launch();      \
+    SVT_CUDA(cudaGetLastError());     \
+  } while (0)
+
 #define SVT_TRY(expr)        \
   do {                       \
     int _s = (expr);         \
@@ -42,6 +49,7 @@ int fail(int code, const std::string& msg);
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+void note_kernel_launch();
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
 
 #ifdef __CUDACC__

@@ -281,7 +281,7 @@ EncPlan make_plan(const svt_encoder* e, int B, int L) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
   p.off_stats = take(64);
-  p.off_chan = take(sizeof(float) * 2 * C * B);
+  p.off_chan = take(sizeof(double) * 2 * C * B);
   const size_t slack = 2 * C * 8 * 2;  // overlapping conv rows read up to (k - stride) * C elements past the end
   p.off_bufA = take(static_cast<size_t>(B) * p.T0a * C * 2 + slack);
   const int T1a = p.T0a / (c.num_conv_layers > 1 ? c.conv_stride[1] : 1);
@@ -322,7 +322,7 @@ static int forward_impl(svt_encoder* e, const float* wav, int B, int L, void* ws
   uint8_t* base = static_cast<uint8_t*>(ws);
   double* stats_in = reinterpret_cast<double*>(base + p.off_stats);
   double* stats_out = stats_in + 2;
-  float* chan = reinterpret_cast<float*>(base + p.off_chan);
+  double* chan = reinterpret_cast<double*>(base + p.off_chan);
   __nv_bfloat16* bufA = reinterpret_cast<__nv_bfloat16*>(base + p.off_bufA);
   __nv_bfloat16* bufB = reinterpret_cast<__nv_bfloat16*>(base + p.off_bufB);
   float* h = reinterpret_cast<float*>(base + p.off_h);

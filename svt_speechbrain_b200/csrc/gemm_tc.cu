@@ -303,7 +303,7 @@ int launch(const GemmArgs& g, const KParams& kp, cudaStream_t stream) {
   const int tiles = kp.m_tiles * kp.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, kp);
-  SVT_CUDA(cudaGetLastError());
+  SVT_POST_LAUNCH();
   return kOk;
 }
 

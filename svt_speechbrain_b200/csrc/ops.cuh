@@ -53,12 +53,12 @@ struct Conv0Args {
   const double* in_stats = nullptr;  // [2] sum, sumsq over the B*L input (null: no input normalisation)
   __nv_bfloat16* out = nullptr;
   int layer_mode = 1;
-  float* chan_stats = nullptr;  // group mode: [B][C][2] fp32 sums (zeroed by the launcher)
+  double* chan_stats = nullptr;  // group mode: [B][C][2] sums (zeroed by the launcher)
 };
 int conv0_forward(const Conv0Args& a, cudaStream_t stream);
 
 // group-norm apply (+GELU) for the base model's layer 0: in-place on (B, t_alloc, C) bf16
-int groupnorm_gelu_apply(__nv_bfloat16* x, const float* chan_stats, const float* gamma, const float* beta, int B, int T,
+int groupnorm_gelu_apply(__nv_bfloat16* x, const double* chan_stats, const float* gamma, const float* beta, int B, int T,
                          int t_alloc, int C, cudaStream_t stream);
 
 // Output whole-tensor norm + head + frame post-processing:

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256)
 conv0_kernel(const float* __restrict__ wav, int L, int T, int t_alloc, const float* __restrict__ w,
              const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
              const double* __restrict__ in_stats, double n_in, __nv_bfloat16* __restrict__ out,
-             float* __restrict__ chan_stats) {
+             double* __restrict__ chan_stats) {
   __shared__ __align__(16) float sw[kK0 * kC0];
   __shared__ __align__(16) float sbias[kC0];
   __shared__ __align__(16) float sgamma[kC0];
@@ -217,21 +217,21 @@ conv0_kernel(const float* __restrict__ wav, int L, int T, int t_alloc, const flo
     }
   }
   if (!kLayerMode) {
-    float* st = chan_stats + static_cast<size_t>(clip) * kC0 * 2;
+    double* st = chan_stats + static_cast<size_t>(clip) * kC0 * 2;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int c = i * 128 + lane * 4 + e;
-        atomicAdd(st + 2 * c, cs[4 * i + e]);
-        atomicAdd(st + 2 * c + 1, css[4 * i + e]);
+        atomicAdd(st + 2 * c, static_cast<double>(cs[4 * i + e]));
+        atomicAdd(st + 2 * c + 1, static_cast<double>(css[4 * i + e]));
       }
   }
 }
 
 // group-norm apply + GELU, in place.  block = 256 threads = 4 frames x 64 channel-octets
 __global__ void __launch_bounds__(256)
-groupnorm_gelu_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ chan_stats,
+groupnorm_gelu_kernel(__nv_bfloat16* __restrict__ x, const double* __restrict__ chan_stats,
                       const float* __restrict__ gamma, const float* __restrict__ beta, int T, int t_alloc, int C,
                       int frames_per_block) {
   const int clip = blockIdx.y;
@@ -240,12 +240,12 @@ groupnorm_gelu_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ c
   float sc[8], sh[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const float* st = chan_stats + (static_cast<size_t>(clip) * C + c0 + e) * 2;
-    const float m = st[0] / T;
-    const float var = fmaxf(st[1] / T - m * m, 0.f);
-    const float rs = rsqrtf(var + 1e-5f);
+    const double* st = chan_stats + (static_cast<size_t>(clip) * C + c0 + e) * 2;
+    const double m = st[0] / T;
+    const double var = fmax(st[1] / T - m * m, 0.0);
+    const float rs = static_cast<float>(1.0 / sqrt(var + 1e-5));
     sc[e] = rs * gamma[c0 + e];
-    sh[e] = beta[c0 + e] - m * sc[e];
+    sh[e] = beta[c0 + e] - static_cast<float>(m) * sc[e];
   }
   const int tbeg = blockIdx.x * frames_per_block;
   for (int t = tbeg + sub; t < tbeg + frames_per_block && t < T; t += 4) {
@@ -397,7 +397,7 @@ int layer_norm(const LayerNormArgs& a, cudaStream_t stream) {
   return dispatch_nv(a.D, [&](auto nv) {
     layer_norm_kernel<decltype(nv)::value><<<ceil_div(a.rows, 8), 256, 0, stream>>>(
         a.x_f32, a.x_bf16, a.gamma, a.beta, a.y_bf16, a.y_f32, a.rows, a.eps, a.gelu, a.stats, clip_rows, clip_valid);
-    SVT_CUDA(cudaGetLastError());
+    SVT_POST_LAUNCH();
     return static_cast<int>(kOk);
   });
 }
@@ -407,7 +407,7 @@ int tensor_stats(const float* x, size_t n, double* stats, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return fail(kInvalidArgument, "tensor_stats: input must be 16-byte aligned");
   const int grid = num_sms() * 4;
   tensor_stats_kernel<<<grid, 256, 0, stream>>>(x, n, stats);
-  SVT_CUDA(cudaGetLastError());
+  SVT_POST_LAUNCH();
   return kOk;
 }
 
@@ -422,21 +422,21 @@ int conv0_forward(const Conv0Args& a, cudaStream_t stream) {
     conv0_kernel<true><<<grid, 256, 0, stream>>>(a.wav, a.L, a.T, a.t_alloc, a.w, a.bias, a.gamma, a.beta, a.in_stats,
                                                  n_in, a.out, nullptr);
   } else {
-    SVT_CUDA(cudaMemsetAsync(a.chan_stats, 0, sizeof(float) * 2 * a.C * a.B, stream));
+    SVT_CUDA(cudaMemsetAsync(a.chan_stats, 0, sizeof(double) * 2 * a.C * a.B, stream));
     conv0_kernel<false><<<grid, 256, 0, stream>>>(a.wav, a.L, a.T, a.t_alloc, a.w, a.bias, nullptr, nullptr, a.in_stats,
                                                   n_in, a.out, a.chan_stats);
   }
-  SVT_CUDA(cudaGetLastError());
+  SVT_POST_LAUNCH();
   return kOk;
 }
 
-int groupnorm_gelu_apply(__nv_bfloat16* x, const float* chan_stats, const float* gamma, const float* beta, int B, int T,
+int groupnorm_gelu_apply(__nv_bfloat16* x, const double* chan_stats, const float* gamma, const float* beta, int B, int T,
                          int t_alloc, int C, cudaStream_t stream) {
   if (C != 512) return fail(kUnsupported, "groupnorm: C must be 512");
   const int fpb = 64;
   dim3 grid(ceil_div(T, fpb), B);
   groupnorm_gelu_kernel<<<grid, 256, 0, stream>>>(x, chan_stats, gamma, beta, T, t_alloc, C, fpb);
-  SVT_CUDA(cudaGetLastError());
+  SVT_POST_LAUNCH();
   return kOk;
 }
 
@@ -457,7 +457,7 @@ int head_forward(const HeadArgs& a, cudaStream_t stream) {
     if (grid > num_sms()) grid = num_sms();
     head_kernel<NV><<<grid, 256, smem, stream>>>(a.x, a.clips, a.clip_rows, a.T, a.stats, a.eps, a.w, a.b, a.n_out,
                                                  a.feats, a.logits, w_in_smem);
-    SVT_CUDA(cudaGetLastError());
+    SVT_POST_LAUNCH();
     return static_cast<int>(kOk);
   });
 }
@@ -467,7 +467,7 @@ int frame_argmax(const float* logits, int n_frames, int n_out, int oct_off, int 
   if (n_frames <= 0) return kOk;
   frame_argmax_kernel<<<ceil_div(n_frames, 256), 256, 0, stream>>>(logits, n_frames, n_out, oct_off, n_oct, pc_off, n_pc,
                                                                   oct, pc);
-  SVT_CUDA(cudaGetLastError());
+  SVT_POST_LAUNCH();
   return kOk;
 }
 
@@ -477,7 +477,7 @@ int pack_bf16(const PackArgs& a, __nv_bfloat16* dst, cudaStream_t stream) {
   pack_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a.src, a.dims[0], a.dims[1], a.dims[2], a.dims[3], a.strides[0],
                                                       a.strides[1], a.strides[2], a.strides[3], a.scale, a.vec,
                                                       a.vec_dim, dst);
-  SVT_CUDA(cudaGetLastError());
+  SVT_POST_LAUNCH();
   return kOk;
 }
 int pack_f32(const PackArgs& a, float* dst, cudaStream_t stream) {
@@ -485,13 +485,13 @@ int pack_f32(const PackArgs& a, float* dst, cudaStream_t stream) {
   const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, 4096));
   pack_kernel<float><<<grid, 256, 0, stream>>>(a.src, a.dims[0], a.dims[1], a.dims[2], a.dims[3], a.strides[0],
                                               a.strides[1], a.strides[2], a.strides[3], a.scale, a.vec, a.vec_dim, dst);
-  SVT_CUDA(cudaGetLastError());
+  SVT_POST_LAUNCH();
   return kOk;
 }
 
 int weight_norm_scale(const float* v, const float* g, int d0, int d1, int taps, float* out, cudaStream_t stream) {
   weight_norm_scale_kernel<<<taps, 256, 0, stream>>>(v, g, d0 * d1, taps, out);
-  SVT_CUDA(cudaGetLastError());
+  SVT_POST_LAUNCH();
   return kOk;
 }
 
@@ -499,18 +499,18 @@ int add_positional_encoding(const float* x, int clips, int T_src, int T, int D, 
                             cudaStream_t stream) {
   dim3 grid(T, clips);
   add_pe_kernel<<<grid, 256, 0, stream>>>(x, T_src, T, D, out_f32, out_bf16);
-  SVT_CUDA(cudaGetLastError());
+  SVT_POST_LAUNCH();
   return kOk;
 }
 
 int add_f32(const float* a, const float* b, float* out, size_t n, cudaStream_t stream) {
   add_f32_kernel<<<num_sms() * 4, 256, 0, stream>>>(a, b, out, n);
-  SVT_CUDA(cudaGetLastError());
+  SVT_POST_LAUNCH();
   return kOk;
 }
 int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, size_t n, cudaStream_t stream) {
   cast_bf16_kernel<<<num_sms() * 4, 256, 0, stream>>>(x, y, n);
-  SVT_CUDA(cudaGetLastError());
+  SVT_POST_LAUNCH();
   return kOk;
 }
 

@@ -39,7 +39,7 @@ def _diagnose(a, w, got, ref):
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 256, 64), (256, 256, 128), (128, 128, 256), (1000, 512, 1536),
                                     (333, 1024, 512), (4096, 3072, 1024), (777, 768, 3072), (2000, 4096, 1024)])
 def test_gemm_plain(M, N, K):
-    from tests.gpu_util import op_gemm, rel_l2
+    from gpu_util import op_gemm, rel_l2
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
     w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
@@ -56,7 +56,7 @@ def test_gemm_plain(M, N, K):
 
 @pytest.mark.parametrize("act", [0, 1, 2])
 def test_gemm_epilogue(act):
-    from tests.gpu_util import op_gemm, rel_l2
+    from gpu_util import op_gemm, rel_l2
     M, N, K = 515, 512, 256
     g = torch.Generator(device="cuda").manual_seed(act)
     a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
@@ -78,7 +78,7 @@ def test_gemm_epilogue(act):
 @pytest.mark.parametrize("k,stride", [(3, 2), (2, 2)])
 def test_gemm_conv_view(k, stride):
     """strided conv1d over channel-last activations as an overlapping-row GEMM view == F.conv1d."""
-    from tests.gpu_util import op_gemm
+    from gpu_util import op_gemm
     C, Tin, B = 512, 400, 2
     Tout = Tin // stride
     g = torch.Generator(device="cuda").manual_seed(k)

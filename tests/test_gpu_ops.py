@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("dh,heads,T,Ta,clips", [(64, 16, 499, 500, 2), (64, 12, 49, 50, 3), (64, 4, 130, 130, 1),
                                                   (128, 8, 499, 499, 2), (128, 8, 64, 64, 1)])
 def test_attention_self(dh, heads, T, Ta, clips):
-    from tests.gpu_util import op_attention, rel_l2
+    from gpu_util import op_attention, rel_l2
     D = heads * dh
     g = torch.Generator(device="cuda").manual_seed(T + dh)
     qkv = torch.randn(clips * Ta, 3 * D, device="cuda", generator=g).bfloat16()
@@ -27,7 +27,7 @@ def test_attention_self(dh, heads, T, Ta, clips):
 
 
 def test_attention_cross():
-    from tests.gpu_util import op_attention, rel_l2
+    from gpu_util import op_attention, rel_l2
     dh, heads, Tq, Tk, clips = 128, 8, 77, 130, 2
     D = heads * dh
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -45,7 +45,7 @@ def test_attention_cross():
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("gelu", [0, 1])
 def test_layer_norm(D, dtype, gelu):
-    from tests.gpu_util import op_layer_norm
+    from gpu_util import op_layer_norm
     g = torch.Generator(device="cuda").manual_seed(D)
     x = (torch.randn(1003, D, device="cuda", generator=g) * 3 + 0.5).to(dtype)
     gamma = torch.randn(D, device="cuda", generator=g)
@@ -55,7 +55,7 @@ def test_layer_norm(D, dtype, gelu):
     if gelu:
         ref = torch.nn.functional.gelu(ref)
     assert (yf - ref).abs().max().item() < 2e-4
-    assert (yb.float() - ref).abs().max().item() < 0.05
+    assert ((yb.float() - ref).abs() / (1.0 + ref.abs())).max().item() < 6e-3  # bf16 rounding, 2^-9 relative
 
 
 def test_conv0_layer_mode():
@@ -76,9 +76,9 @@ def test_conv0_layer_mode():
     xn = torch.nn.functional.layer_norm(wav, wav.shape)
     ref = torch.nn.functional.conv1d(xn[:, None], w, bias, stride=5).transpose(1, 2)
     ref = torch.nn.functional.gelu(torch.nn.functional.layer_norm(ref, (512,), gamma, beta, 1e-5))
-    err = (out[:, :T].float() - ref).abs().max().item()
-    print("conv0 max abs err", err)
-    assert err < 0.03  # bf16 output rounding of O(1..4) values
+    err = ((out[:, :T].float() - ref).abs() / (1.0 + ref.abs())).max().item()
+    print("conv0 max scaled err", err)
+    assert err < 6e-3  # bf16 output rounding (2^-9 relative) plus fp32 arithmetic differences
     assert (out[:, T:] == 0).all()
 
 

@@ -20,6 +20,7 @@ constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kNumEpiWarps = 8;
+constexpr int kEpiStageBytes = 4096;
 
 template <int BN>
 struct Cfg {
@@ -28,7 +29,8 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator stages (power of two)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kNumEpiWarps * kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct KParams {
@@ -51,7 +53,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle atoms need 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* stage_area = smem + C::kStages * C::kStageBytes;  // 8 epilogue warps x 4 KB transpose tiles
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_area + kNumEpiWarps * kEpiStageBytes);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tfull_bar = empty_bar + C::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -143,6 +146,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ epilogue
     const int quad = warp & 3;
     const int half = (warp - kEpiWarp0) >> 2;
+    uint8_t* stage_mine = stage_area + (warp - kEpiWarp0) * kEpiStageBytes;
     constexpr int kColsPerWarp = BN / 2;
     int as = 0;
     uint32_t aphase = 0;
@@ -159,10 +163,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         row0 = clip * p.clip_rows + tt * BM;
         valid = p.clip_valid - tt * BM;
       }
-      const int r_in_tile = quad * 32 + lane;
-      const bool row_ok = r_in_tile < valid;
-      const size_t row = static_cast<size_t>(row0 + r_in_tile);
-
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
 #pragma unroll 1
@@ -194,32 +194,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
         }
-        if (row_ok) {
-          const size_t off = row * static_cast<size_t>(p.ld_out) + static_cast<size_t>(col);
-          if (p.resid != nullptr) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.resid + off);
+        // Thread = row in TMEM, but HBM wants lanes along columns: transpose the 32 x 32 chunk through this
+        // warp's private XOR-swizzled staging tile (conflict-free both ways), then do coalesced row segments.
+        if (p.out_f32 != nullptr || p.resid != nullptr) {
+          float* st = reinterpret_cast<float*>(stage_mine);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (4 * j < nv) {
-                const float4 q = r4[j];
-                v[4 * j + 0] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(st + lane * 32 + ((q ^ (lane & 7)) << 2)) =
+                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+          const int c4 = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3);
+            float4 a = *reinterpret_cast<const float4*>(st + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+            if (quad * 32 + rr < valid && 4 * c4 < nv) {
+              const size_t off = static_cast<size_t>(row0 + quad * 32 + rr) * static_cast<size_t>(p.ld_out) +
+                                 static_cast<size_t>(col + 4 * c4);
+              if (p.resid != nullptr) {
+                const float4 q = *reinterpret_cast<const float4*>(p.resid + off);
+                a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
               }
+              if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + off) = a;
+              if (p.out_bf16 != nullptr)
+                *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
             }
           }
-          if (p.out_f32 != nullptr) {
-            float4* o4 = reinterpret_cast<float4*>(p.out_f32 + off);
+          __syncwarp();
+        } else {
+          uint8_t* st = stage_mine;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (4 * j < nv) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (p.out_bf16 != nullptr) {
-            uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + off);
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(st + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                           pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+          __syncwarp();
+          const int sl = lane & 3;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (8 * j < nv)
-                o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                     pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + (lane >> 2);
+            const uint4 a = *reinterpret_cast<const uint4*>(st + rr * 64 + ((sl ^ ((rr >> 1) & 3)) << 4));
+            if (quad * 32 + rr < valid && 8 * sl < nv)
+              *reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(row0 + quad * 32 + rr) * static_cast<size_t>(p.ld_out) +
+                                        static_cast<size_t>(col + 8 * sl)) = a;
           }
+          __syncwarp();
         }
       }
       // all of this warp's TMEM reads are complete (wait::ld above) -> release the accumulator stage
@@ -256,6 +275,8 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+}  // namespace
+
 int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                     const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
@@ -283,6 +304,8 @@ int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t
   }
   return kOk;
 }
+
+namespace {
 
 template <int BN>
 int launch(const GemmArgs& g, const KParams& kp, cudaStream_t stream) {

@@ -46,4 +46,8 @@ struct GemmArgs {
 
 int gemm_bf16_tc(const GemmArgs& g, cudaStream_t stream);
 
+// bf16 tiled tensor map with 128-byte swizzle; strides in elements for dims 1..rank-1
+int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                    const uint32_t* box);
+
 }  // namespace svt

@@ -99,3 +99,22 @@ def test_linear_small_and_postproc():
     torch.cuda.synchronize()
     assert torch.equal(octv.long(), lg[:, 2:7].argmax(1)) and torch.equal(pc.long(), lg[:, 7:20].argmax(1))
     assert octv[3].item() == 0
+
+
+def test_gelu_accuracy():
+    """The fused epilogue GELU (exact-erf form, A&S 7.1.26 erfc) against float64 erf GELU, via LN(gelu=1) with
+    identity affine on rows engineered to be already normalised."""
+    import math
+    from gpu_util import op_layer_norm
+    D = 1024
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(512, D, device="cuda", generator=g) * 2.5
+    x = (x - x.mean(1, keepdim=True)) / x.var(1, unbiased=False, keepdim=True).add(1e-5).sqrt()
+    gamma = torch.full((D,), 3.0, device="cuda")  # spread the arguments over (-12, 12)
+    beta = torch.zeros(D, device="cuda")
+    yf, _ = op_layer_norm(x, gamma, beta, 1e-5, 1)
+    z = torch.nn.functional.layer_norm(x.double(), (D,), gamma.double(), beta.double(), 1e-5)
+    ref = 0.5 * z * (1 + torch.erf(z / math.sqrt(2)))
+    err = (yf.double() - ref).abs().max().item()
+    print("gelu max abs err vs float64 erf-GELU", err)
+    assert err < 5e-6

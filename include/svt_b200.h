@@ -46,6 +46,10 @@ int svt_device_count(void);
 /* kernels launched by this library since it was loaded (all streams); used by bench.py's gpu_launches */
 long long svt_debug_launch_count(void);
 
+/* process-wide tuning / test switches.  "attention_impl": 0 auto (default), 1 force the mma.sync kernel,
+ * 2 force the tcgen05/TMEM kernel (head_dim 64 only). */
+int svt_set_option(const char* name, int value);
+
 /* ------------------------------------------------------------------ wav2vec2-style SSL encoder + head */
 typedef struct svt_encoder svt_encoder;
 

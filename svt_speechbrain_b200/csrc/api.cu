@@ -15,6 +15,8 @@ int fail(int code, const std::string& msg) {
 static std::atomic<long long> g_launches{0};
 void note_kernel_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(); }
+static std::atomic<int> g_attention_impl{0};
+int get_option_attention_impl() { return g_attention_impl.load(std::memory_order_relaxed); }
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -35,6 +37,16 @@ extern "C" {
 int svt_version(void) { return 100; }
 long long svt_debug_launch_count(void) { return launch_count(); }
 const char* svt_last_error(void) { return g_last_error.c_str(); }
+int svt_set_option(const char* name, int value) {
+  if (name == nullptr) return fail(kInvalidArgument, "null argument");
+  const std::string n(name);
+  if (n == "attention_impl") {
+    if (value < 0 || value > 2) return fail(kInvalidArgument, "attention_impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
+    g_attention_impl.store(value);
+    return kOk;
+  }
+  return fail(kInvalidArgument, "unknown option " + n);
+}
 int svt_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {

@@ -245,6 +245,9 @@ int launch_attention(const AttentionArgs& a, cudaStream_t stream) {
 int attention_bf16(const AttentionArgs& a, cudaStream_t stream) {
   if (a.Tq <= 0 || a.Tk <= 0 || a.clips <= 0 || a.heads <= 0) return fail(kInvalidArgument, "attention: empty problem");
   if ((a.ldq | a.ldk | a.ldv) % 8 != 0 || a.ldo % 2 != 0) return fail(kInvalidArgument, "attention: misaligned leading dims");
+  const int impl = get_option_attention_impl();
+  if (impl == 2 && a.head_dim != 64) return fail(kUnsupported, "attention: the tcgen05 kernel is built for head_dim 64");
+  if (a.head_dim == 64 && impl != 1 && a.ldo % 8 == 0) return attention_bf16_tc(a, stream);
   if (a.head_dim == 64) return launch_attention<64>(a, stream);
   if (a.head_dim == 128) return launch_attention<128>(a, stream);
   return fail(kUnsupported, "attention: head_dim must be 64 or 128");

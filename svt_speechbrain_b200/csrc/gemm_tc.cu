@@ -163,13 +163,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         row0 = clip * p.clip_rows + tt * BM;
         valid = p.clip_valid - tt * BM;
       }
+      // pull the NEXT tile's residual rows towards L2 while this tile is processed (the fp32 residual stream is
+      // the only operand of this kernel that does not arrive through TMA)
+      if (p.resid != nullptr) {
+        const int nt = tile + gridDim.x;
+        if (nt < num_tiles) {
+          const int nn = nt % p.n_tiles, nm = nt / p.n_tiles;
+          int nrow0, nvalid;
+          if (p.mode == 0) { nrow0 = nm * BM; nvalid = p.M - nrow0; }
+          else { const int cl = nm / p.tiles_per_clip, tt = nm % p.tiles_per_clip; nrow0 = cl * p.clip_rows + tt * BM; nvalid = p.clip_valid - tt * BM; }
+          constexpr int kLinesPerRow = BN * 4 / 128;
+          const int et = threadIdx.x - kEpiWarp0 * 32;
+          for (int i = et; i < BM * kLinesPerRow; i += kNumEpiWarps * 32) {
+            const int r = i / kLinesPerRow, l = i % kLinesPerRow;
+            if (r < nvalid && l * 32 < p.n_valid)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + static_cast<size_t>(nrow0 + r) * p.ld_out + nn * p.n_stride + l * 32));
+          }
+        }
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
+      const bool f32_path = (p.out_f32 != nullptr || p.resid != nullptr);
+      const int c4 = lane & 7;
 #pragma unroll 1
       for (int c = 0; c < kColsPerWarp; c += 32) {
         const int col_in_tile = half * kColsPerWarp + c;
         const int col = n_tile * p.n_stride + col_in_tile;
         const int nv = p.n_valid - col_in_tile;  // valid columns of this 32-wide chunk
+        // residual chunk in the coalesced store mapping (lane = 4 columns of row 4i + lane/8), all eight loads
+        // issued before the TMEM read so their latency overlaps it (resid may alias out_f32: loads come first)
+        float4 rs[8];
+        if (p.resid != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3);
+            rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (quad * 32 + rr < valid && 4 * c4 < nv)
+              rs[i] = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row0 + quad * 32 + rr) * static_cast<size_t>(p.ld_out) +
+                                                       static_cast<size_t>(col + 4 * c4));
+          }
+        }
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN + col_in_tile),
                   r);
@@ -196,14 +229,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // Thread = row in TMEM, but HBM wants lanes along columns: transpose the 32 x 32 chunk through this
         // warp's private XOR-swizzled staging tile (conflict-free both ways), then do coalesced row segments.
-        if (p.out_f32 != nullptr || p.resid != nullptr) {
+        if (f32_path) {
           float* st = reinterpret_cast<float*>(stage_mine);
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(st + lane * 32 + ((q ^ (lane & 7)) << 2)) =
                 make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           __syncwarp();
-          const int c4 = lane & 7;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = 4 * i + (lane >> 3);
@@ -211,10 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (quad * 32 + rr < valid && 4 * c4 < nv) {
               const size_t off = static_cast<size_t>(row0 + quad * 32 + rr) * static_cast<size_t>(p.ld_out) +
                                  static_cast<size_t>(col + 4 * c4);
-              if (p.resid != nullptr) {
-                const float4 q = *reinterpret_cast<const float4*>(p.resid + off);
-                a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
-              }
+              if (p.resid != nullptr) { a.x += rs[i].x; a.y += rs[i].y; a.z += rs[i].z; a.w += rs[i].w; }
               if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + off) = a;
               if (p.out_bf16 != nullptr)
                 *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));

@@ -15,7 +15,10 @@ struct AttentionArgs {
   int q_clip_rows = 0, k_clip_rows = 0; // allocated rows per clip
   int clips = 0, heads = 0, head_dim = 0;
 };
-int attention_bf16(const AttentionArgs& a, cudaStream_t stream);
+int attention_bf16(const AttentionArgs& a, cudaStream_t stream);       // dispatcher
+int attention_bf16_tc(const AttentionArgs& a, cudaStream_t stream);    // tcgen05 / TMEM kernel (attention_tc.cu), head_dim 64
+// process-wide options (svt_set_option): "attention_impl" 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 kernel
+int get_option_attention_impl();
 
 // ---- row ops (rowops.cu)
 // y = LayerNorm(x) over the last dim (biased variance), optional GELU afterwards.

@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Per-kernel timings of the hot path's shapes at BASELINE config 2 (B=64, 10-s clips), CUDA events, L2 flushed
+between launches.  Prints one line per kernel: us/launch, TFLOP/s or GB/s.  Development tool (not bench.py)."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from svt_speechbrain_b200._lib import check, current_stream_ptr, lib, ptr  # noqa: E402
+
+dev = torch.device("cuda", 0)
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, n=8, warm=2):
+    ts = []
+    for i in range(warm + n):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= warm:
+            ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def gemm(name, M, N, K, act=0, resid=False, f32=False, k_inner=None, row_stride=None, out=None):
+    a = torch.randn(M + 8, K if row_stride is None else row_stride, device=dev).bfloat16()
+    w = torch.randn(N, K, device=dev).bfloat16()
+    bias = torch.zeros(N, device=dev)
+    h = torch.randn(M, N, device=dev) if (resid or f32) else None
+    ob = torch.empty(M, N, device=dev, dtype=torch.bfloat16) if not (resid or f32) else None
+    s = current_stream_ptr()
+    rs = K if row_stride is None else row_stride
+    ki = K if k_inner is None else k_inner
+    fn = lambda: check(lib().svt_op_gemm(ptr(a), rs, ki, ptr(w), ptr(bias), ptr(h) if resid else None, ptr(h), ptr(ob), M, N, K, N, act, s))
+    us = timeit(fn)
+    tf = 2.0 * M * N * K / us / 1e6
+    print(f"{name:34s} M={M:8d} N={N:5d} K={K:5d}  {us:9.1f} us  {tf:7.1f} TFLOP/s", flush=True)
+    if out is not None:
+        out[name] = {"us": us, "tflops": tf}
+
+
+def attention(name, impl, clips, heads, T, Ta, dh, out=None):
+    D = heads * dh
+    qkv = torch.randn(clips * Ta, 3 * D, device=dev).bfloat16()
+    o = torch.zeros(clips * Ta, D, device=dev, dtype=torch.bfloat16)
+    check(lib().svt_set_option(b"attention_impl", impl))
+    s = current_stream_ptr()
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    fn = lambda: check(lib().svt_op_attention(ptr(q), ptr(k), ptr(v), ptr(o), 3 * D, 3 * D, 3 * D, D, T, T, Ta, Ta, clips, heads, dh, s))
+    us = timeit(fn)
+    check(lib().svt_set_option(b"attention_impl", 0))
+    tf = 4.0 * clips * heads * T * T * dh / us / 1e6
+    print(f"{name:34s} clips={clips} heads={heads} T={T} dh={dh}  {us:9.1f} us  {tf:7.1f} TFLOP/s", flush=True)
+    if out is not None:
+        out[name] = {"us": us, "tflops": tf}
+
+
+def layer_norm(name, rows, D, src_f32, gelu, out=None):
+    x = torch.randn(rows, D, device=dev)
+    if not src_f32:
+        x = x.bfloat16()
+    g, b = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    y = torch.empty(rows, D, device=dev, dtype=torch.bfloat16)
+    s = current_stream_ptr()
+    fn = lambda: check(lib().svt_op_layer_norm(ptr(x) if src_f32 else None, None if src_f32 else ptr(x), ptr(g), ptr(b), ptr(y), None, rows, D, 1e-5, gelu, s))
+    us = timeit(fn)
+    gb = rows * D * ((4 if src_f32 else 2) + 2) / us / 1e3
+    print(f"{name:34s} rows={rows:8d} D={D}  {us:9.1f} us  {gb:7.1f} GB/s", flush=True)
+    if out is not None:
+        out[name] = {"us": us, "gbs": gb}
+
+
+def main():
+    out = {}
+    B, T, Ta = 64, 499, 500
+    M = B * Ta
+    which = sys.argv[1:] or ["gemm", "attn", "ln", "conv"]
+    if "gemm" in which:
+        gemm("qkv (bf16 out)", M, 3072, 1024, out=out)
+        gemm("out-proj (+resid fp32)", M, 1024, 1024, resid=True, out=out)
+        gemm("ffn1 (gelu, bf16 out)", M, 4096, 1024, act=1, out=out)
+        gemm("ffn2 (+resid fp32)", M, 1024, 4096, resid=True, out=out)
+        gemm("proj 512->1024 (fp32 out)", M, 1024, 512, f32=True, out=out)
+    if "conv" in which:
+        gemm("conv1 k3s2 (implicit)", 1024000, 512, 1536, k_inner=512, row_stride=1024, out=out)
+        gemm("conv2 k3s2 (implicit)", 512000, 512, 1536, k_inner=512, row_stride=1024, out=out)
+        gemm("conv5 k2s2 (implicit)", 64000, 512, 1024, k_inner=512, row_stride=1024, out=out)
+    if "attn" in which:
+        attention("attention mma.sync dh64", 1, B, 16, T, Ta, 64, out=out)
+        attention("attention tcgen05 dh64", 2, B, 16, T, Ta, 64, out=out)
+        attention("attention mma.sync dh128 (fusion)", 1, 8, 8, T, Ta, 128, out=out)
+    if "ln" in which:
+        layer_norm("LN 1024 fp32->bf16", M, 1024, True, 0, out=out)
+        layer_norm("LN 512 bf16->bf16 +gelu (conv1)", 1024000, 512, False, 1, out=out)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "kernel_bench.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,10 @@ long long svt_debug_launch_count(void);
  * 2 force the tcgen05/TMEM kernel (head_dim 64 only). */
 int svt_set_option(const char* name, int value);
 
+/* development aid: device buffer of 4 x 256 int64 that CTA 0 of the tcgen05 attention kernel fills with clock64()
+ * stamps of its pipeline phases (NULL switches it off, the default); see tools/attention_trace.py */
+void svt_debug_attention_trace(void* dev_buffer_8k);
+
 /* ------------------------------------------------------------------ wav2vec2-style SSL encoder + head */
 typedef struct svt_encoder svt_encoder;
 

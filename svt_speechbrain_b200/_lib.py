@@ -40,6 +40,7 @@ _SIGS = {
     "svt_device_count": (C.c_int, []),
     "svt_debug_launch_count": (C.c_longlong, []),
     "svt_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "svt_debug_attention_trace": (None, [_P]),
     "svt_encoder_create": (C.c_int, [C.POINTER(EncoderConfig), C.POINTER(_P)]),
     "svt_encoder_destroy": (None, [_P]),
     "svt_encoder_set_tensor": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, C.c_int]),

@@ -47,6 +47,7 @@ int svt_set_option(const char* name, int value) {
   }
   return fail(kInvalidArgument, "unknown option " + n);
 }
+void svt_debug_attention_trace(void* dev_buffer_8k) { set_attention_trace_buffer(static_cast<long long*>(dev_buffer_8k)); }
 int svt_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {

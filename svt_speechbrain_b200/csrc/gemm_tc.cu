@@ -85,16 +85,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * C::kStageBytes;
-          uint8_t* sb = sa + C::kABytes;
+    // The whole warp walks the (warp-uniform) loop so that addresses and coordinates live in uniform registers;
+    // one elected lane arms the barrier and issues the copies.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int clip = m_tile / p.tiles_per_clip;
+      const int tt = m_tile % p.tiles_per_clip;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * C::kStageBytes;
+        uint8_t* sb = sa + C::kABytes;
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
           if (p.mode == 0) {
             const int k0 = kb * BK;
@@ -102,33 +106,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d(sb, &tmB, &full_bar[stage], k0, n_tile * BN);
           } else {
             // positional conv: group = n_tile, tap = kb; frames shifted by (tap - pad_left), OOB -> 0
-            const int clip = m_tile / p.tiles_per_clip;
-            const int tt = m_tile % p.tiles_per_clip;
             tma_load_3d(sa, &tmA, &full_bar[stage], n_tile * p.n_stride, tt * BM + kb - p.pad_left, clip);
             tma_load_2d(sb, &tmB, &full_bar[stage], 0, (n_tile * p.num_kb + kb) * BN);
           }
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-          const uint64_t da = make_sw128_kmajor_desc(sa);
-          const uint64_t db = make_sw128_kmajor_desc(sa + C::kABytes);
+        const uint64_t da = make_sw128_kmajor_desc(smem_base + stage * C::kStageBytes);
+        const uint64_t db = make_sw128_kmajor_desc(smem_base + stage * C::kStageBytes + C::kABytes);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in 16-byte units
@@ -136,11 +139,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                       (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (kb == p.num_kb - 1) umma_commit(&tfull_bar[as]);  // accumulator complete
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
+      if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------------ epilogue

@@ -19,6 +19,8 @@ int attention_bf16(const AttentionArgs& a, cudaStream_t stream);       // dispat
 int attention_bf16_tc(const AttentionArgs& a, cudaStream_t stream);    // tcgen05 / TMEM kernel (attention_tc.cu), head_dim 64
 // process-wide options (svt_set_option): "attention_impl" 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 kernel
 int get_option_attention_impl();
+// development aid: device buffer of 4 x 256 int64 clock stamps written by CTA 0 of the tcgen05 attention kernel
+void set_attention_trace_buffer(long long* dev_ptr);
 
 // ---- row ops (rowops.cu)
 // y = LayerNorm(x) over the last dim (biased variance), optional GELU afterwards.

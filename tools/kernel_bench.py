@@ -50,7 +50,9 @@ def gemm(name, M, N, K, act=0, resid=False, f32=False, k_inner=None, row_stride=
 
 def attention(name, impl, clips, heads, T, Ta, dh, out=None):
     D = heads * dh
-    qkv = torch.randn(clips * Ta, 3 * D, device=dev).bfloat16()
+    qkv = torch.randn(clips * Ta, 3 * D, device=dev)
+    qkv[:, :D] *= dh ** -0.5  # the packed q-projection carries the 1/sqrt(d_h) scale
+    qkv = qkv.bfloat16()
     o = torch.zeros(clips * Ta, D, device=dev, dtype=torch.bfloat16)
     check(lib().svt_set_option(b"attention_impl", impl))
     s = current_stream_ptr()

@@ -47,7 +47,8 @@ int svt_device_count(void);
 long long svt_debug_launch_count(void);
 
 /* process-wide tuning / test switches.  "attention_impl": 0 auto (default), 1 force the mma.sync kernel,
- * 2 force the tcgen05/TMEM kernel (head_dim 64 only). */
+ * 2 force the tcgen05/TMEM kernel (head_dim 64 only).  "gemm_impl": 0 auto (CTA-pair cta_group::2 kernel when
+ * N % 256 == 0), 1 force the one-CTA kernel. */
 int svt_set_option(const char* name, int value);
 
 /* development aid: device buffer of 4 x 256 int64 that CTA 0 of the tcgen05 attention kernel fills with clock64()

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <mutex>
 
+#include "gemm_epilogue.cuh"
 #include "model.cuh"
 
 namespace svt {
@@ -16,6 +17,8 @@ static std::atomic<long long> g_launches{0};
 void note_kernel_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(); }
 static std::atomic<int> g_attention_impl{0};
+static std::atomic<int> g_gemm_impl{0};
+int get_option_gemm_impl() { return g_gemm_impl.load(std::memory_order_relaxed); }
 int get_option_attention_impl() { return g_attention_impl.load(std::memory_order_relaxed); }
 int num_sms() {
   static int sms = 0;
@@ -43,6 +46,11 @@ int svt_set_option(const char* name, int value) {
   if (n == "attention_impl") {
     if (value < 0 || value > 2) return fail(kInvalidArgument, "attention_impl must be 0 (auto), 1 (mma.sync) or 2 (tcgen05)");
     g_attention_impl.store(value);
+    return kOk;
+  }
+  if (n == "gemm_impl") {
+    if (value < 0 || value > 1) return fail(kInvalidArgument, "gemm_impl must be 0 (auto) or 1 (one-CTA kernel)");
+    g_gemm_impl.store(value);
     return kOk;
   }
   return fail(kInvalidArgument, "unknown option " + n);

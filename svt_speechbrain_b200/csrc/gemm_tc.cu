@@ -8,6 +8,7 @@
 //   warps 2-3   : idle (keep the epilogue warps aligned to TMEM lane quadrants: warp_id % 4)
 //   warps 4-11  : epilogue; warp w owns TMEM lanes 32*(w%4).. and column half (w-4)/4 of the tile
 #include "gemm_tc.cuh"
+#include "gemm_epilogue.cuh"
 
 #include <mutex>
 
@@ -18,9 +19,6 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kThreads = 384;
-constexpr int kEpiWarp0 = 4;
-constexpr int kNumEpiWarps = 8;
-constexpr int kEpiStageBytes = 4096;
 
 template <int BN>
 struct Cfg {
@@ -39,11 +37,7 @@ struct KParams {
   int tiles_per_clip, clip_rows, clip_valid, pad_left;
   int n_stride;  // output-column (and posconv input-channel) offset per n-tile
   int n_valid;   // valid output columns per n-tile (<= BN)
-  const float* bias;
-  const float* resid;
-  float* out_f32;
-  __nv_bfloat16* out_bf16;
-  int ld_out, act;
+  GemmEpiParams e;
 };
 
 template <int BN>
@@ -151,7 +145,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quad = warp & 3;
     const int half = (warp - kEpiWarp0) >> 2;
     uint8_t* stage_mine = stage_area + (warp - kEpiWarp0) * kEpiStageBytes;
-    constexpr int kColsPerWarp = BN / 2;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -167,113 +160,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         row0 = clip * p.clip_rows + tt * BM;
         valid = p.clip_valid - tt * BM;
       }
-      // pull the NEXT tile's residual rows towards L2 while this tile is processed (the fp32 residual stream is
-      // the only operand of this kernel that does not arrive through TMA)
-      if (p.resid != nullptr) {
+      // pull the NEXT tile's residual rows towards L2 while this tile is processed
+      if (p.e.resid != nullptr) {
         const int nt = tile + gridDim.x;
         if (nt < num_tiles) {
           const int nn = nt % p.n_tiles, nm = nt / p.n_tiles;
           int nrow0, nvalid;
           if (p.mode == 0) { nrow0 = nm * BM; nvalid = p.M - nrow0; }
           else { const int cl = nm / p.tiles_per_clip, tt = nm % p.tiles_per_clip; nrow0 = cl * p.clip_rows + tt * BM; nvalid = p.clip_valid - tt * BM; }
-          constexpr int kLinesPerRow = BN * 4 / 128;
-          const int et = threadIdx.x - kEpiWarp0 * 32;
-          for (int i = et; i < BM * kLinesPerRow; i += kNumEpiWarps * 32) {
-            const int r = i / kLinesPerRow, l = i % kLinesPerRow;
-            if (r < nvalid && l * 32 < p.n_valid)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + static_cast<size_t>(nrow0 + r) * p.ld_out + nn * p.n_stride + l * 32));
-          }
+          gemm_prefetch_resid<BN>(p.e, nrow0, nvalid, nn * p.n_stride, p.n_valid);
         }
       }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const bool f32_path = (p.out_f32 != nullptr || p.resid != nullptr);
-      const int c4 = lane & 7;
-#pragma unroll 1
-      for (int c = 0; c < kColsPerWarp; c += 32) {
-        const int col_in_tile = half * kColsPerWarp + c;
-        const int col = n_tile * p.n_stride + col_in_tile;
-        const int nv = p.n_valid - col_in_tile;  // valid columns of this 32-wide chunk
-        // residual chunk in the coalesced store mapping (lane = 4 columns of row 4i + lane/8), all eight loads
-        // issued before the TMEM read so their latency overlaps it (resid may alias out_f32: loads come first)
-        float4 rs[8];
-        if (p.resid != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + (lane >> 3);
-            rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (quad * 32 + rr < valid && 4 * c4 < nv)
-              rs[i] = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row0 + quad * 32 + rr) * static_cast<size_t>(p.ld_out) +
-                                                       static_cast<size_t>(col + 4 * c4));
-          }
-        }
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN + col_in_tile),
-                  r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (4 * j < nv) {
-              const float4 b = __ldg(b4 + j);
-              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            }
-          }
-        }
-        if (p.act == kActGelu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        } else if (p.act == kActRelu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        }
-        // Thread = row in TMEM, but HBM wants lanes along columns: transpose the 32 x 32 chunk through this
-        // warp's private XOR-swizzled staging tile (conflict-free both ways), then do coalesced row segments.
-        if (f32_path) {
-          float* st = reinterpret_cast<float*>(stage_mine);
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(st + lane * 32 + ((q ^ (lane & 7)) << 2)) =
-                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + (lane >> 3);
-            float4 a = *reinterpret_cast<const float4*>(st + rr * 32 + ((c4 ^ (rr & 7)) << 2));
-            if (quad * 32 + rr < valid && 4 * c4 < nv) {
-              const size_t off = static_cast<size_t>(row0 + quad * 32 + rr) * static_cast<size_t>(p.ld_out) +
-                                 static_cast<size_t>(col + 4 * c4);
-              if (p.resid != nullptr) { a.x += rs[i].x; a.y += rs[i].y; a.z += rs[i].z; a.w += rs[i].w; }
-              if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + off) = a;
-              if (p.out_bf16 != nullptr)
-                *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-            }
-          }
-          __syncwarp();
-        } else {
-          uint8_t* st = stage_mine;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(st + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
-                make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                           pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
-          __syncwarp();
-          const int sl = lane & 3;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = 8 * i + (lane >> 2);
-            const uint4 a = *reinterpret_cast<const uint4*>(st + rr * 64 + ((sl ^ ((rr >> 1) & 3)) << 4));
-            if (quad * 32 + rr < valid && 8 * sl < nv)
-              *reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(row0 + quad * 32 + rr) * static_cast<size_t>(p.ld_out) +
-                                        static_cast<size_t>(col + 8 * sl)) = a;
-          }
-          __syncwarp();
-        }
-      }
+      gemm_epilogue_tile<BN>(p.e, row0, valid, n_tile * p.n_stride, p.n_valid, tmem_base + static_cast<uint32_t>(as * BN), quad,
+                             half, lane, stage_mine);
       // all of this warp's TMEM reads are complete (wait::ld above) -> release the accumulator stage
       tc_fence_before();
       __syncwarp();
@@ -366,18 +267,20 @@ int launch(const GemmArgs& g, const KParams& kp, cudaStream_t stream) {
 }  // namespace
 
 int gemm_bf16_tc(const GemmArgs& g, cudaStream_t stream) {
+  if (get_option_gemm_impl() != 1 && gemm_pair_supported(g) && g.M >= 1024) return gemm_bf16_tc_pair(g, stream);
   KParams kp{};
   kp.mode = g.mode;
   kp.M = g.M;
   kp.N = g.N;
   kp.K = g.K;
   kp.k_inner = g.k_inner > 0 ? g.k_inner : g.K;
-  kp.bias = g.bias;
-  kp.resid = g.resid;
-  kp.out_f32 = g.out_f32;
-  kp.out_bf16 = g.out_bf16;
-  kp.ld_out = g.ld_out;
-  kp.act = g.act;
+  kp.e.M = g.M;
+  kp.e.bias = g.bias;
+  kp.e.resid = g.resid;
+  kp.e.out_f32 = g.out_f32;
+  kp.e.out_bf16 = g.out_bf16;
+  kp.e.ld_out = g.ld_out;
+  kp.e.act = g.act;
   if (g.mode == 0 && (g.K % BK != 0 || kp.k_inner % BK != 0))
     return fail(kInvalidArgument, "gemm: K must be a multiple of 64");
   if (g.ld_out % 8 != 0) return fail(kInvalidArgument, "gemm: ld_out must be a multiple of 8");

@@ -1,0 +1,261 @@
+// CTA-pair variant of the bf16 GEMM (cta_group::2): two CTAs of one cluster (the two SMs of a TPC) share every
+// MMA.  One 256 x 256 output tile per pair and step: CTA r stages A rows [128 r, 128 r + 128) and W rows
+// [128 r, 128 r + 128) of the tile; the leader's single thread issues tcgen05.mma.cta_group::2 (M = 256,
+// N = 256, K = 16), which reads both CTAs' shared memory and writes accumulator rows [128 r, +128) into CTA r's
+// TMEM.  Compared with the one-CTA kernel (gemm_tc.cu) each SM stages and reads half of the B operand:
+// shared-memory traffic per SM drops from 96 + 96 B/clk (TMA fill + MMA reads) to 64 + 64 B/clk, which is what
+// capped the one-CTA kernel near 80 % of the tensor peak; the smaller stage also buys a 6-deep ring.
+//
+// Barrier protocol (all mbarriers live at the same shared-memory offsets in both CTAs):
+//   full[s]   (leader's copy only)  : armed by the leader's producer with the bytes of BOTH CTAs; both producers'
+//                                     TMA loads complete_tx on it (cp.async.bulk.tensor ... cta_group::2)
+//   empty[s]  (each CTA's own copy) : tcgen05.commit ... multicast::cluster from the leader's MMA thread
+//   tfull[a]  (each CTA's own copy) : multicast commit after the last k-block of a tile
+//   tempty[a] (leader's copy only)  : 2 x 8 epilogue warps arrive (the peer's through shared::cluster)
+// Roles per CTA as in gemm_tc.cu: warp 0 TMA producer, warp 1 TMEM allocator (+ MMA issuer in the leader),
+// warps 4-11 epilogue over the CTA's own 128 accumulator rows.
+#include "gemm_tc.cuh"
+#include "gemm_epilogue.cuh"
+
+namespace svt {
+
+namespace {
+
+constexpr int BM = 128;   // rows per CTA (256 per pair)
+constexpr int BN2 = 256;  // columns per pair tile
+constexpr int BK = 64;
+constexpr int kThreads = 384;
+constexpr int kStages2 = 6;
+constexpr int kABytes = BM * BK * 2;         // 16 KB
+constexpr int kBBytes = (BN2 / 2) * BK * 2;  // 16 KB: this CTA's half of the W tile
+constexpr int kStageBytes2 = kABytes + kBBytes;
+constexpr int kTmemCols2 = 512;              // two accumulator stages of 256 columns
+constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + kNumEpiWarps * kEpiStageBytes + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior MMAs of this thread retire) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmEpiParams p,
+                int k_inner, int num_kb, int m_pairs, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_area = smem + kStages2 * kStageBytes2;  // 8 epilogue warps x 4 KB transpose tiles
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_area + kNumEpiWarps * kEpiStageBytes);
+  uint64_t* empty_bar = full_bar + kStages2;
+  uint64_t* tfull_bar = empty_bar + kStages2;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_tiles = m_pairs * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * kNumEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair<kTmemCols2>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised and its TMEM is allocated before anything touches them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int n_tile = tile % n_tiles;
+      const int m_row = ((tile / n_tiles) * 2 + static_cast<int>(rank)) * BM;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * kStageBytes2;
+        uint8_t* sb = sa + kABytes;
+        const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes2);
+          const int k0 = kb * BK;
+          tma_load_3d_pair(sa, &tmA, leader_full, k0 % k_inner, k0 / k_inner, m_row);
+          tma_load_2d_pair(sb, &tmB, leader_full, k0, n_tile * BN2 + static_cast<int>(rank) * (BN2 / 2));
+        }
+        __syncwarp();
+        if (++stage == kStages2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN2);
+      const uint32_t smem_base = smem_u32(smem);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);  // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_sw128_kmajor_desc(smem_base + stage * kStageBytes2);
+          const uint64_t db = make_sw128_kmajor_desc(smem_base + stage * kStageBytes2 + kABytes);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_pair(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                             (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == num_kb - 1) umma_commit_pair(&tfull_bar[as]);
+          }
+          __syncwarp();
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+    const int quad = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;
+    uint8_t* stage_mine = stage_area + (warp - kEpiWarp0) * kEpiStageBytes;
+    const uint32_t leader_tempty0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int n_tile = tile % n_tiles;
+      const int row0 = ((tile / n_tiles) * 2 + static_cast<int>(rank)) * BM;
+      const int valid = p.M - row0;
+      if (p.resid != nullptr) {
+        const int nt = tile + num_pairs;
+        if (nt < num_tiles) {
+          const int nrow0 = ((nt / n_tiles) * 2 + static_cast<int>(rank)) * BM;
+          gemm_prefetch_resid<BN2>(p, nrow0, p.M - nrow0, (nt % n_tiles) * BN2, BN2);
+        }
+      }
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      gemm_epilogue_tile<BN2>(p, row0, valid, n_tile * BN2, BN2, tmem_base + static_cast<uint32_t>(as * BN2), quad, half, lane,
+                              stage_mine);
+      // all of this warp's TMEM reads are complete -> release the accumulator stage to the leader's MMA thread
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_tempty0 + static_cast<uint32_t>(as * 8));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody exits (or frees TMEM) while the peer can still read its smem or signal its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair<kTmemCols2>(tmem_base);
+  }
+}
+
+}  // namespace
+
+bool gemm_pair_supported(const GemmArgs& g) {
+  return g.mode == 0 && g.N % BN2 == 0 && g.K % BK == 0 && (g.k_inner > 0 ? g.k_inner : g.K) % BK == 0 && num_sms() % 2 == 0;
+}
+
+int gemm_bf16_tc_pair(const GemmArgs& g, cudaStream_t stream) {
+  if (!gemm_pair_supported(g)) return fail(kUnsupported, "gemm (cta pair): needs N % 256 == 0 and K % 64 == 0");
+  if (g.ld_out % 8 != 0) return fail(kInvalidArgument, "gemm: ld_out must be a multiple of 8");
+  GemmEpiParams p{};
+  p.M = g.M; p.bias = g.bias; p.resid = g.resid; p.out_f32 = g.out_f32; p.out_bf16 = g.out_bf16;
+  p.ld_out = g.ld_out; p.act = g.act;
+  const int k_inner = g.k_inner > 0 ? g.k_inner : g.K;
+  CUtensorMap tmA, tmB;
+  const uint32_t abox[3] = {BK, 1, BM};
+  SVT_TRY(encode_bf16_map(&tmA, g.a, 3, g.a_dims, g.a_strides, abox));
+  const uint64_t wd[2] = {static_cast<uint64_t>(g.w_cols), static_cast<uint64_t>(g.w_rows)};
+  const uint64_t ws[1] = {static_cast<uint64_t>(g.w_cols)};
+  const uint32_t wb[2] = {BK, BN2 / 2};
+  SVT_TRY(encode_bf16_map(&tmB, g.w, 2, wd, ws, wb));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SVT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+    attr_set = true;
+  }
+  const int m_pairs = ceil_div(g.M, 2 * BM);
+  const int n_tiles = g.N / BN2;
+  const int tiles = m_pairs * n_tiles;
+  const int max_pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
+  gemm_tc2_kernel<<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles);
+  SVT_POST_LAUNCH();
+  return kOk;
+}
+
+}  // namespace svt

@@ -1,0 +1,89 @@
+"""CTA-pair (cta_group::2) tcgen05 GEMM (csrc/gemm_tc2.cu) vs torch fp32 matmul and vs the one-CTA kernel.
+Own file = own process in tools/run_gpu_checks.sh."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _set_impl(v):
+    from svt_speechbrain_b200._lib import check, lib
+    check(lib().svt_set_option(b"gemm_impl", v))
+
+
+@pytest.fixture(autouse=True)
+def _restore_impl():
+    yield
+    _set_impl(0)
+
+
+def _ref(a, w, bias, resid, act):
+    y = a.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    if act == 1:
+        y = torch.nn.functional.gelu(y)
+    elif act == 2:
+        y = torch.relu(y)
+    if resid is not None:
+        y = y + resid
+    return y
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 256, 64), (1024, 256, 256), (1280, 512, 1536), (2381, 1024, 512), (4096, 3072, 1024),
+                                    (32000, 1024, 1024), (1025, 768, 3072), (40000, 512, 128)])
+def test_pair_gemm_plain(M, N, K):
+    from gpu_util import op_gemm, rel_l2
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    _set_impl(0)
+    of, ob = op_gemm(a, w, out_f32=True, out_bf16=True)
+    ref = _ref(a, w, None, None, 0)
+    err = (of - ref).abs().max().item()
+    print(f"pair gemm {M}x{N}x{K}: max abs err fp32 out {err:.3e}, rel_l2 {rel_l2(of, ref):.3e}")
+    if not err < 2e-3:
+        ok = ((of - ref).abs() < 2e-3)
+        print("fraction ok", ok.float().mean().item(), "nan frac", torch.isnan(of).float().mean().item())
+        print("ok by 128-row block:", ok.float().mean(1)[: 128 * 16].view(-1, 128).mean(1).tolist())
+        print("ok by 64-col block:", ok.float().mean(0).view(-1, 64).mean(1).tolist())
+    assert torch.isfinite(of).all()
+    assert err < 2e-3, err
+    assert rel_l2(ob.float(), ref) < 4e-3
+    _set_impl(1)
+    of1, _ = op_gemm(a, w, out_f32=True, out_bf16=False)
+    assert (of - of1).abs().max().item() < 1e-3  # same products, same fp32 accumulation order per k-block
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_pair_gemm_epilogue(act):
+    from gpu_util import op_gemm, rel_l2
+    M, N, K = 1539, 512, 256
+    g = torch.Generator(device="cuda").manual_seed(act)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    of, ob = op_gemm(a, w, bias=bias, resid=resid, out_f32=True, out_bf16=True, act=act)
+    ref = _ref(a, w, bias, resid, act)
+    assert (of - ref).abs().max().item() < 3e-3
+    assert rel_l2(ob.float(), ref) < 4e-3
+    of2, ob2 = op_gemm(a, w, bias=bias, out_f32=False, out_bf16=True, act=act)  # bf16-only store path
+    assert rel_l2(ob2.float(), _ref(a, w, bias, None, act)) < 4e-3
+
+
+@pytest.mark.parametrize("k,stride", [(3, 2), (2, 2)])
+def test_pair_gemm_conv_view(k, stride):
+    """strided conv1d as implicit GEMM over overlapping channel-last rows, through the pair kernel"""
+    from gpu_util import op_gemm
+    C, T_in = 512, 4001
+    T_out = (T_in - k) // stride + 1
+    g = torch.Generator(device="cuda").manual_seed(k)
+    x = torch.randn(T_in + 8, C, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(C, C, k, device="cuda", generator=g) / (C * k) ** 0.5).bfloat16()
+    wp = w.permute(0, 2, 1).contiguous().view(C, k * C)
+    of, _ = op_gemm(x, wp, out_f32=True, out_bf16=False, a_row_stride=stride * C, k_inner=C, M=T_out)
+    ref = torch.nn.functional.conv1d(x[:T_in].float().t().unsqueeze(0), w.float(), stride=stride)[0].t()
+    err = (of - ref).abs().max().item()
+    print(f"pair conv view k={k} s={stride}: max abs err {err:.3e}")
+    assert err < 2e-3

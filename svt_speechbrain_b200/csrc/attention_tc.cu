@@ -100,10 +100,6 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void turn_wait(int t) { asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory"); }
 __device__ __forceinline__ void turn_pass(int t) { asm volatile("bar.arrive %0, 256;" ::"r"(2 - t) : "memory"); }
 
-template <int kRegs>
-__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
-template <int kRegs>
-__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
 // keys >= n_valid of the last block do not exist (TMA zero-filled them): set their scores to -inf once, so that the
 // row max ignores them and 2^(-inf) = 0 drops them from P and from the row sum (n_valid is warp-uniform)

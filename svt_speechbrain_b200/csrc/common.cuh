@@ -169,6 +169,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld that also "redefines" the 32 destination registers of an earlier tmem_ld32, so the compiler cannot read
+// (or copy) them before the wait: lets a TMEM load stay in flight across unrelated work (software pipelining).
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
 // SM100 shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of exactly 128 B
 // (64 bf16): 8-row core groups 1024 B apart (SBO), LBO unused by the swizzled K-major form.
@@ -188,21 +203,25 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 }
 
 // Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)), written as relu(x) - 0.5 |x| erfc(|x| / sqrt 2) with
-// erfc(a) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-a^2), t = 1 / (1 + p a)  (Abramowitz-Stegun 7.1.26,
-// |erf error| <= 1.5e-7): 2 MUFU + ~12 FMA-pipe instructions instead of libm erff's ~40, abs error < 4e-7
-// (torch's own fp32 GELU is 1.2e-6 from the exact value) -- see tests/test_gpu_ops.py::test_gelu_accuracy.
+// erfc(z) = (1 + a1 z + ... + a6 z^6)^-16  (Abramowitz-Stegun 7.1.28, |erf error| <= 3e-7; the 1/sqrt 2 is folded
+// into the coefficients): 6 FFMA + ONE MUFU (rcp) + 4 squarings + 3, abs error < 8e-7 over the whole real line
+// (torch's own fp32 GELU is ~1e-6 from the exact value) -- tests/test_gpu_ops.py::test_gelu_accuracy.
+// One MUFU instead of libm erff's or 7.1.26's two matters: the GEMM epilogues that apply it are MUFU-bound.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x);
-  const float a = ax * 0.70710678118654752f;
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.0f)));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a * a * -1.4426950408889634f));
-  return fmaxf(x, 0.0f) - 0.5f * ax * (p * e);
+  float p = fmaf(5.38297490493278e-06f, ax, 4.889063711743802e-05f);
+  p = fmaf(p, ax, 3.8003574445610866e-05f);
+  p = fmaf(p, ax, 0.0032776263542473316f);
+  p = fmaf(p, ax, 0.02114100567996502f);
+  p = fmaf(p, ax, 0.04986734688282013f);
+  p = fmaf(p, ax, 1.0f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
+  r *= r;
+  r *= r;
+  r *= r;
+  r *= r;
+  return fmaf(-0.5f * ax, r, fmaxf(x, 0.0f));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

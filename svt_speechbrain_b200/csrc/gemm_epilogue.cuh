@@ -26,7 +26,7 @@ struct GemmEpiParams {
 template <int BN>
 __device__ __forceinline__ void gemm_prefetch_resid(const GemmEpiParams& p, int row0, int valid, int col0, int n_valid) {
   constexpr int kLinesPerRow = BN * 4 / 128;
-  const int et = threadIdx.x - kEpiWarp0 * 32;
+  const int et = static_cast<int>(threadIdx.x) % (kNumEpiWarps * 32);  // epilogue warps are physical warps 0-7
   for (int i = et; i < 128 * kLinesPerRow; i += kNumEpiWarps * 32) {
     const int r = i / kLinesPerRow, l = i % kLinesPerRow;
     if (r < valid && l * 32 < n_valid)
@@ -34,68 +34,98 @@ __device__ __forceinline__ void gemm_prefetch_resid(const GemmEpiParams& p, int 
   }
 }
 
+__device__ __forceinline__ void epi_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 epi_lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// This warp's slice of the bias for one tile (BN / 2 columns, 4 per lane), fetched one tile ahead of its use.
+template <int BN>
+__device__ __forceinline__ float4 gemm_load_bias_slice(const GemmEpiParams& p, int col0, int n_valid, int half, int lane) {
+  const int c = half * (BN / 2) + 4 * lane;
+  if (p.bias == nullptr || 4 * lane >= BN / 2 || c >= n_valid) return make_float4(0.f, 0.f, 0.f, 0.f);
+  return __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c));
+}
+
 // row0 / valid: first output row of this CTA's 128-row tile and how many of its rows exist; col0 / n_valid: first
-// output column and valid columns of the tile; tmem_acc: TMEM address (lane 0) of the accumulator stage.
+// output column and valid columns of the tile; tmem_acc: TMEM address (lane 0) of the accumulator stage;
+// stage_addr: shared-space address of this warp's 4 KB staging tile; bias4: gemm_load_bias_slice of this tile.
+//
+// Thread = row in TMEM, but HBM wants lanes along columns, so every 32 x 32 chunk is transposed through the warp's
+// private XOR-swizzled staging tile (conflict-free both ways) and leaves as whole row segments:
+//   bf16-only outputs : bias (broadcast reads of the slice parked in the upper half of the staging tile) and
+//                       activation on the row-per-thread registers, packed bf16 through 2 KB of staging;
+//   fp32 / residual   : raw accumulators through 4 KB of staging, then bias, activation and the fp32 residual
+//                       (prefetched ahead of the TMEM read) in the coalesced mapping, where a lane keeps the
+//                       same 4 columns for all 8 of its rows.
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int row0, int valid, int col0, int n_valid,
-                                                   uint32_t tmem_acc, int quad, int half, int lane, uint8_t* stage_mine) {
+                                                   uint32_t tmem_acc, int quad, int half, int lane, uint32_t stage_addr,
+                                                   float4 bias4) {
   constexpr int kColsPerWarp = BN / 2;
   const bool f32_path = (p.out_f32 != nullptr || p.resid != nullptr);
   const int c4 = lane & 7;
+  const uint32_t bias_slot = stage_addr + 2048;
+  if (!f32_path && p.bias != nullptr) {
+    if (4 * lane < kColsPerWarp)
+      epi_sts128(bias_slot + 16 * lane, __float_as_uint(bias4.x), __float_as_uint(bias4.y), __float_as_uint(bias4.z),
+                 __float_as_uint(bias4.w));
+    __syncwarp();
+  }
+  // the TMEM read of chunk c + 1 is issued before the math of chunk c and stays in flight under it
+  const uint32_t tmem_row = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(half * kColsPerWarp);
+  uint32_t rn[32];
+  tmem_ld32(tmem_row, rn);
 #pragma unroll 1
   for (int c = 0; c < kColsPerWarp; c += 32) {
     const int col_in_tile = half * kColsPerWarp + c;
     const int col = col0 + col_in_tile;
     const int nv = n_valid - col_in_tile;  // valid columns of this 32-wide chunk
-    // residual chunk in the coalesced store mapping (lane = 4 columns of row 4i + lane/8), all eight loads
-    // issued before the TMEM read so their latency overlaps it (resid may alias out_f32: loads come first)
-    float4 rs[8];
-    if (p.resid != nullptr) {
+    if (f32_path) {
+      // residual + bias of this chunk in the coalesced mapping (lane = 4 columns of rows 4i + lane / 8), all loads
+      // issued before the TMEM read so their latency overlaps it (resid may alias out_f32: loads come first)
+      float4 rs[8];
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias != nullptr && 4 * c4 < nv) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4 * c4));
+      if (p.resid != nullptr) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = 4 * i + (lane >> 3);
-        rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (quad * 32 + rr < valid && 4 * c4 < nv)
-          rs[i] = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row0 + quad * 32 + rr) * static_cast<size_t>(p.ld_out) +
-                                                   static_cast<size_t>(col + 4 * c4));
-      }
-    }
-    uint32_t r[32];
-    tmem_ld32(tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(col_in_tile), r);
-    tmem_ld_wait();
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (p.bias != nullptr) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (4 * j < nv) {
-          const float4 b = __ldg(b4 + j);
-          v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3);
+          rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (quad * 32 + rr < valid && 4 * c4 < nv)
+            rs[i] = *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row0 + quad * 32 + rr) * static_cast<size_t>(p.ld_out) +
+                                                     static_cast<size_t>(col + 4 * c4));
         }
       }
-    }
-    if (p.act == kActGelu) {
+      uint32_t r[32];
+      tmem_ld_wait_regs(rn);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-    } else if (p.act == kActRelu) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-    }
-    // Thread = row in TMEM, but HBM wants lanes along columns: transpose the 32 x 32 chunk through this
-    // warp's private XOR-swizzled staging tile (conflict-free both ways), then do coalesced row segments.
-    if (f32_path) {
-      float* st = reinterpret_cast<float*>(stage_mine);
+      for (int j = 0; j < 32; ++j) r[j] = rn[j];
+      if (c + 32 < kColsPerWarp) tmem_ld32(tmem_row + c + 32, rn);
 #pragma unroll
       for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<float4*>(st + lane * 32 + ((q ^ (lane & 7)) << 2)) =
-            make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        epi_sts128(stage_addr + lane * 128 + ((q ^ (lane & 7)) << 4), r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
       __syncwarp();
+      uint4 raw[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = 4 * i + (lane >> 3);
-        float4 a = *reinterpret_cast<const float4*>(st + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+        raw[i] = epi_lds128(stage_addr + rr * 128 + ((c4 ^ (rr & 7)) << 4));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + (lane >> 3);
+        float4 a = make_float4(__uint_as_float(raw[i].x) + b4.x, __uint_as_float(raw[i].y) + b4.y,
+                               __uint_as_float(raw[i].z) + b4.z, __uint_as_float(raw[i].w) + b4.w);
+        if (p.act == kActGelu) {
+          a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
+        } else if (p.act == kActRelu) {
+          a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+        }
         if (quad * 32 + rr < valid && 4 * c4 < nv) {
           const size_t off = static_cast<size_t>(row0 + quad * 32 + rr) * static_cast<size_t>(p.ld_out) +
                              static_cast<size_t>(col + 4 * c4);
@@ -107,21 +137,45 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
       }
       __syncwarp();
     } else {
-      uint8_t* st = stage_mine;
+      tmem_ld_wait_regs(rn);
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rn[j]);
+      if (c + 32 < kColsPerWarp) tmem_ld32(tmem_row + c + 32, rn);
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 b = epi_lds128(bias_slot + (c + 4 * j) * 4);  // same address in every lane: broadcast
+          v[4 * j + 0] += __uint_as_float(b.x); v[4 * j + 1] += __uint_as_float(b.y);
+          v[4 * j + 2] += __uint_as_float(b.z); v[4 * j + 3] += __uint_as_float(b.w);
+        }
+      }
+      if (p.act == kActGelu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      } else if (p.act == kActRelu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<uint4*>(st + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
-            make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                       pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+        epi_sts128(stage_addr + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), pack_bf16x2(v[8 * q], v[8 * q + 1]),
+                   pack_bf16x2(v[8 * q + 2], v[8 * q + 3]), pack_bf16x2(v[8 * q + 4], v[8 * q + 5]),
+                   pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
       __syncwarp();
       const int sl = lane & 3;
+      uint4 o[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int rr = 8 * i + (lane >> 2);
-        const uint4 a = *reinterpret_cast<const uint4*>(st + rr * 64 + ((sl ^ ((rr >> 1) & 3)) << 4));
+        o[i] = epi_lds128(stage_addr + rr * 64 + ((sl ^ ((rr >> 1) & 3)) << 4));
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = 8 * i + (lane >> 2);
         if (quad * 32 + rr < valid && 8 * sl < nv)
           *reinterpret_cast<uint4*>(p.out_bf16 + static_cast<size_t>(row0 + quad * 32 + rr) * static_cast<size_t>(p.ld_out) +
-                                    static_cast<size_t>(col + 8 * sl)) = a;
+                                    static_cast<size_t>(col + 8 * sl)) = o[i];
       }
       __syncwarp();
     }

@@ -91,6 +91,13 @@ def main():
         gemm("out-proj (+resid fp32)", M, 1024, 1024, resid=True, out=out)
         gemm("ffn1 (gelu, bf16 out)", M, 4096, 1024, act=1, out=out)
         gemm("ffn2 (+resid fp32)", M, 1024, 4096, resid=True, out=out)
+        if "variants" in which:
+            gemm("ffn1 shape, no act", M, 4096, 1024, act=0, out=out)
+            gemm("ffn1 shape, relu", M, 4096, 1024, act=2, out=out)
+            gemm("ffn1 shape, gelu, K=2048", M, 4096, 2048, act=1, out=out)
+            gemm("ffn1 shape, no act, K=2048", M, 4096, 2048, act=0, out=out)
+            gemm("qkv shape K=256", M, 3072, 256, act=0, out=out)
+            gemm("qkv shape gelu K=256", M, 3072, 256, act=1, out=out)
         gemm("proj 512->1024 (fp32 out)", M, 1024, 512, f32=True, out=out)
     if "conv" in which:
         gemm("conv1 k3s2 (implicit)", 1024000, 512, 1536, k_inner=512, row_stride=1024, out=out)

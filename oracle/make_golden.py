@@ -171,6 +171,29 @@ def gold_frame2note():
     print("frame2note cases", len(cases))
 
 
+def gold_avhubert_resnet(name, B, T, seed=5):
+    """Reference ResEncoder (N20EMv2/video_only/resnet.py:133-171) on seeded weights (avhubert_oracle.random_weights,
+    BN with non-trivial running statistics) and a seeded normalised-video-like input."""
+    from .avhubert_oracle import AVHubertConfig, random_weights as av_weights
+
+    sd = av_weights(AVHubertConfig(encoder_layers=0), seed=seed)
+    pre = "model.feature_extractor_video.resnet."
+    ref = rb.reference_res_encoder()
+    own = ref.state_dict()
+    for k in own:
+        if k.endswith("num_batches_tracked"):
+            continue
+        own[k] = sd[pre + k]
+    ref.load_state_dict(own, strict=True)
+    g = torch.Generator().manual_seed(seed + 100)
+    video = torch.randn(B, 1, T, 88, 88, generator=g)
+    with torch.no_grad():
+        out = ref(video)  # (B, 512, T)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), B=B, T=T, weight_seed=seed, video_seed=seed + 100,
+                        out=out.numpy())
+    print(name, tuple(out.shape), "absmax", float(out.abs().max()))
+
+
 def main():
     assert rb.available(), "needs /root/reference"
     os.makedirs(GOLD, exist_ok=True)
@@ -185,6 +208,7 @@ def main():
     gold_fusion("fusion_full", D=1024, d_ffn=3072, nhead=8, B=1, Ta=49, Tv=50, store_weights=False)
     gold_fusion("fusion_full_pad", D=1024, d_ffn=3072, nhead=8, B=2, Ta=49, Tv=45, store_weights=False)
     gold_frame2note()
+    gold_avhubert_resnet("avhubert_resnet_b2_t6", B=2, T=6)
 
 
 if __name__ == "__main__":

@@ -84,6 +84,16 @@ def reference_fusion(**kw):
     return FusionRCA(**kw).eval()
 
 
+def reference_res_encoder():
+    """The reference's own lip front end, N20EMv2/video_only/resnet.py:133 (needs only torch)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_video_resnet", os.path.join(REF_ROOT, "N20EMv2", "video_only", "resnet.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.ResEncoder(relu_type="prelu", weights=None).eval()
+
+
 def reference_frame2note():
     setup_paths()
     import importlib.util

@@ -72,3 +72,31 @@ def test_fusion_full_seeded(name):
     v = torch.randn(int(g["B"]), int(g["Tv"]), D, generator=gen)
     out = fo.fusion_forward(sd, a, v, nhead=int(g["nhead"]))
     np.testing.assert_allclose(out.numpy(), g["out"], atol=5e-5, rtol=1e-4)
+
+
+def test_avhubert_resnet_vs_reference_golden():
+    """oracle/avhubert_oracle.res_encoder against the reference's own resnet.ResEncoder (N20EMv2/video_only/resnet.py)
+    run by oracle/make_golden.py on seeded weights / input."""
+    from oracle import avhubert_oracle as av
+
+    d = np.load(os.path.join(GOLD, "avhubert_resnet_b2_t6.npz"))
+    sd = av.random_weights(av.AVHubertConfig(encoder_layers=0), seed=int(d["weight_seed"]))
+    g = torch.Generator().manual_seed(int(d["video_seed"]))
+    video = torch.randn(int(d["B"]), 1, int(d["T"]), 88, 88, generator=g)
+    with torch.no_grad():
+        out = av.res_encoder(sd, video, "model.feature_extractor_video.resnet.")
+    assert out.shape == (2, 512, 6)
+    assert float((out - torch.from_numpy(d["out"])).abs().max()) < 1e-4
+
+
+def test_avhubert_tiny_forward_shapes_and_key_translation():
+    from oracle import avhubert_oracle as av
+
+    cfg = av.AVHubertConfig(encoder_embed_dim=128, encoder_layers=2, encoder_attention_heads=2, encoder_ffn_embed_dim=256,
+                            conv_pos=16, conv_pos_groups=4)
+    sd = av.random_weights(cfg, seed=1)
+    assert "model.encoder.layers.1.self_attn_layer_norm.weight" in sd and "model.encoder.pos_conv.0.weight_g" in sd
+    video = torch.randn(1, 1, 5, 88, 88, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        y = av.lobe_forward(cfg, sd, video)
+    assert y.shape == (1, 5, 128) and abs(float(y.mean())) < 1e-4 and abs(float(y.var(unbiased=False)) - 1.0) < 1e-3

@@ -126,6 +126,38 @@ size_t svt_fusion_workspace_bytes(const svt_fusion* f, int batch, int t_audio);
 int svt_fusion_forward(svt_fusion* f, const float* audio_dev, const float* video_dev, int batch, int t_audio,
                        int t_video, void* workspace_dev, size_t workspace_bytes, float* out_dev, void* stream);
 
+/* ------------------------------------------------------------------ AV-HuBERT video stream (lip ROIs -> features) */
+/* Replaces FairseqAVHubertPretrain.forward({"video": x, "audio": None})  N20EMv2/video_only/fairseq_interface.py:454-485
+ * = AVHubertModel.extract_finetune (hubert.py:688-739): ResEncoder (resnet.py:133-171) -> Linear 512->D -> concat with a
+ * zero audio stream -> LayerNorm(2D) -> Linear 2D->D -> fairseq TransformerEncoder (layer_norm_first) -> output LN. */
+typedef struct svt_video svt_video;
+typedef struct svt_video_config {
+  int embed_dim;        /* cfg.encoder_embed_dim: 1024 (large) */
+  int num_layers;       /* cfg.encoder_layers: 24 */
+  int num_heads;        /* cfg.encoder_attention_heads: 16 */
+  int ffn_size;         /* cfg.encoder_ffn_embed_dim: 4096 */
+  int conv_pos;         /* cfg.conv_pos: 128 */
+  int conv_pos_groups;  /* cfg.conv_pos_groups: 16 */
+  float layer_norm_eps; /* 1e-5 */
+  int input_norm;       /* wrapper's input_norm: F.layer_norm(video, video.shape), fairseq_interface.py:473-474 */
+  int output_norm;      /* wrapper's output_norm: F.layer_norm(out, out.shape),     fairseq_interface.py:482-483 */
+} svt_video_config;
+
+int svt_video_create(const svt_video_config* cfg, svt_video** out);
+void svt_video_destroy(svt_video* v);
+/* fp32 HOST tensors under the reference module's state_dict names ("model." prefix optional):
+ * feature_extractor_video.resnet.{frontend3D,trunk}.*, feature_extractor_video.proj.*, layer_norm.*, post_extract_proj.*,
+ * encoder.{pos_conv.0.*, layers.N.{self_attn.*, self_attn_layer_norm.*, fc1.*, fc2.*, final_layer_norm.*}, layer_norm.*}.
+ * Tensors the video-only forward never reads (feature_extractor_audio.*, mask_emb, final_proj, ...) are ignored. */
+int svt_video_set_tensor(svt_video* v, const char* name, const float* host, const int64_t* shape, int ndim, int strict);
+/* folds every BatchNorm into its conv, packs bf16 kernel layouts */
+int svt_video_finalize(svt_video* v);
+size_t svt_video_workspace_bytes(const svt_video* v, int batch, int n_frames);
+/* video_dev: (B, 1, T, 88, 88) fp32 device (already cropped / normalised as in video_only/train_video_ssl.py:445-457);
+ * feats_dev: (B, T, D) fp32 device.  Asynchronous on `stream`. */
+int svt_video_forward(svt_video* v, const float* video_dev, int batch, int n_frames, void* workspace_dev, size_t workspace_bytes,
+                      float* feats_dev, void* stream);
+
 /* ------------------------------------------------------------------ frame post-processing + note decoding */
 /* logits_dev (n_frames, n_out) fp32 device -> octave / pitch-class argmax (first maximum wins, torch
  * semantics) into int32 device arrays.  Columns [oct_off, oct_off+n_oct) and [pc_off, pc_off+n_pc). */

@@ -25,6 +25,12 @@ class FusionConfig(C.Structure):
     _fields_ = [("d_model", C.c_int), ("nhead", C.c_int), ("d_ffn", C.c_int), ("alpha", C.c_float)]
 
 
+class VideoConfig(C.Structure):
+    _fields_ = [("embed_dim", C.c_int), ("num_layers", C.c_int), ("num_heads", C.c_int), ("ffn_size", C.c_int),
+                ("conv_pos", C.c_int), ("conv_pos_groups", C.c_int), ("layer_norm_eps", C.c_float),
+                ("input_norm", C.c_int), ("output_norm", C.c_int)]
+
+
 class SvtError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libsvt_b200 error {code}: {msg}")
@@ -56,6 +62,12 @@ _SIGS = {
     "svt_fusion_finalize": (C.c_int, [_P]),
     "svt_fusion_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
     "svt_fusion_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P, _P]),
+    "svt_video_create": (C.c_int, [C.POINTER(VideoConfig), C.POINTER(_P)]),
+    "svt_video_destroy": (None, [_P]),
+    "svt_video_set_tensor": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, C.c_int]),
+    "svt_video_finalize": (C.c_int, [_P]),
+    "svt_video_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
+    "svt_video_forward": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P, _P]),
     "svt_frame_postproc": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "svt_frame2note": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_double, C.c_double, C.c_double, _P, C.c_int,
                                  C.POINTER(C.c_int)]),

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsvt_b200.so")
-SOURCES = ["api.cu", "gemm_tc.cu", "gemm_tc2.cu", "attention.cu", "attention_tc.cu", "rowops.cu", "encoder.cu", "fusion.cu", "decode.cpp"]
+SOURCES = ["api.cu", "gemm_tc.cu", "gemm_tc2.cu", "attention.cu", "attention_tc.cu", "rowops.cu", "encoder.cu", "fusion.cu", "video.cu", "decode.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-x", "cu", "-cudart", "static",

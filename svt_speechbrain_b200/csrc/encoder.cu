@@ -144,7 +144,10 @@ int svt_encoder::t_alloc0(int L) const {
 }
 
 // ------------------------------------------------------------------------------------ packing
-static int finalize_impl(svt_encoder* e) {
+namespace svt {
+int encoder_finalize(svt_encoder* e);
+}
+int svt::encoder_finalize(svt_encoder* e) {
   const svt_encoder_config& c = e->cfg;
   const int D = c.hidden_size, F = c.ffn_size, C = c.conv_dim;
   e->pool.release();
@@ -153,6 +156,7 @@ static int finalize_impl(svt_encoder* e) {
   const WeightRegistry& reg = e->reg;
   const RawTensor* t;
 
+  if (!e->transformer_only) {
   // conv layer 0: (C, 1, k) -> [k][C] fp32
   const std::string fe = "feature_extractor.conv_layers.";
   SVT_TRY(reg.require(fe + "0.conv.weight", {C, 1, c.conv_kernel[0]}, &t));
@@ -190,6 +194,7 @@ static int finalize_impl(svt_encoder* e) {
   }
   SVT_TRY(pack_norm(pool, reg, "feature_projection.layer_norm.", C, &e->proj_norm));
   SVT_TRY(pack_linear(pool, reg, "feature_projection.projection.", D, C, &e->proj));
+  }  // !transformer_only
 
   // positional conv: weight-norm recomposition folded here (HF:343-355), packed per (group, tap)
   {
@@ -309,6 +314,93 @@ int linear(const __nv_bfloat16* a, int M, const LinearW& w, const float* resid, 
 }
 }  // namespace
 
+// ------------------------------------------------------------------------------------ transformer body
+// positional conv embedding + N encoder layers + final / per-layer LayerNorms (HF:658-803), shared by the audio
+// encoder and the AV-HuBERT video stream (fairseq TransformerEncoder, same graph).  In: h (fp32 residual stream) and
+// hb (its bf16 copy), rows = clip * Ta + t.  Out: *final_x points at the fp32 rows to normalise / hand to the head;
+// if stats_out != nullptr it receives sum / sum-of-squares of those rows over t < T (whole-tensor output norm).
+namespace svt {
+int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, const TransformerBuffers& tb, double* stats_out,
+                                const float** final_x_out, cudaStream_t s) {
+  const svt_encoder_config& c = e->cfg;
+  const int D = c.hidden_size, H = c.num_heads, dh = D / H;
+  const int M = B * Ta;
+  const float eps = c.layer_norm_eps;
+  float* h = tb.h;
+  __nv_bfloat16* hb = tb.hb;
+  __nv_bfloat16* qkv = tb.qkv;
+  __nv_bfloat16* ctx = tb.ctx;
+  __nv_bfloat16* mid = tb.mid;
+  float* pre = tb.pre;
+  const bool want_stats = stats_out != nullptr;
+  // ---- positional conv embedding + residual: h += GELU(conv(h) + b)
+  {
+    GemmArgs g;
+    g.mode = 1;
+    g.a = hb;
+    g.a_dims[0] = D; g.a_dims[1] = T; g.a_dims[2] = B;
+    g.a_strides[0] = D; g.a_strides[1] = static_cast<uint64_t>(Ta) * D;
+    g.w = e->pos_w; g.w_rows = c.pos_conv_groups * c.pos_conv_kernel * 64; g.w_cols = 64;
+    g.N = D; g.K = c.pos_conv_kernel * 64;
+    g.n_clips = B; g.clip_rows = Ta; g.clip_valid = T; g.pad_left = c.pos_conv_kernel / 2; g.taps = c.pos_conv_kernel;
+    g.group_size = D / c.pos_conv_groups;
+    g.bias = e->pos_b; g.resid = h; g.out_f32 = h; g.ld_out = D; g.act = kActGelu;
+    SVT_TRY(gemm_bf16_tc(g, s));
+  }
+  SVT_CUDA(cudaMemsetAsync(ctx, 0, static_cast<size_t>(M) * D * 2, s));  // rows t >= T are never written by attention
+
+  auto ln_rows = [&](const float* x, const NormW& w, __nv_bfloat16* yb, float* yf, double* stats) {
+    LayerNormArgs ln;
+    ln.x_f32 = x; ln.gamma = w.g; ln.beta = w.b; ln.y_bf16 = yb; ln.y_f32 = yf;
+    ln.rows = M; ln.D = D; ln.eps = eps; ln.stats = stats; ln.clip_rows = Ta; ln.clip_valid = T;
+    return layer_norm(ln, s);
+  };
+  auto attend = [&]() {
+    AttentionArgs a;
+    a.q = qkv; a.k = qkv + D; a.v = qkv + 2 * D; a.o = ctx;
+    a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
+    a.Tq = T; a.Tk = T; a.q_clip_rows = Ta; a.k_clip_rows = Ta; a.clips = B; a.heads = H; a.head_dim = dh;
+    return attention_bf16(a, s);
+  };
+  if (want_stats) SVT_CUDA(cudaMemsetAsync(stats_out, 0, 2 * sizeof(double), s));
+  const float* final_x = nullptr;
+
+  if (c.stable_layer_norm) {
+    // pre-LN layers (HF:612-655) + final encoder LN (HF:792)
+    for (int l = 0; l < c.num_layers; ++l) {
+      const svt_encoder::Layer& Lw = e->layers[l];
+      SVT_TRY(ln_rows(h, Lw.ln1, hb, nullptr, nullptr));
+      SVT_TRY(linear(hb, M, Lw.qkv, nullptr, nullptr, qkv, kActNone, s));
+      SVT_TRY(attend());
+      SVT_TRY(linear(ctx, M, Lw.out, h, h, nullptr, kActNone, s));
+      SVT_TRY(ln_rows(h, Lw.ln2, hb, nullptr, nullptr));
+      SVT_TRY(linear(hb, M, Lw.ff1, nullptr, nullptr, mid, kActGelu, s));
+      SVT_TRY(linear(mid, M, Lw.ff2, h, h, nullptr, kActNone, s));
+    }
+    SVT_TRY(ln_rows(h, e->enc_norm, nullptr, pre, want_stats ? stats_out : nullptr));
+    final_x = pre;
+  } else {
+    // post-LN layers (HF:576-609), encoder LN before the stack (HF:692)
+    const bool no_layers = c.num_layers == 0;
+    SVT_TRY(ln_rows(h, e->enc_norm, hb, h, (want_stats && no_layers) ? stats_out : nullptr));
+    for (int l = 0; l < c.num_layers; ++l) {
+      const svt_encoder::Layer& Lw = e->layers[l];
+      const bool last = l == c.num_layers - 1;
+      SVT_TRY(linear(hb, M, Lw.qkv, nullptr, nullptr, qkv, kActNone, s));
+      SVT_TRY(attend());
+      SVT_TRY(linear(ctx, M, Lw.out, h, h, nullptr, kActNone, s));
+      SVT_TRY(ln_rows(h, Lw.ln1, hb, h, nullptr));
+      SVT_TRY(linear(hb, M, Lw.ff1, nullptr, nullptr, mid, kActGelu, s));
+      SVT_TRY(linear(mid, M, Lw.ff2, h, h, nullptr, kActNone, s));
+      SVT_TRY(ln_rows(h, Lw.ln2, hb, h, (want_stats && last) ? stats_out : nullptr));
+    }
+    final_x = h;
+  }
+  *final_x_out = final_x;
+  return kOk;
+}
+}  // namespace svt
+
 // ------------------------------------------------------------------------------------ forward
 static int forward_impl(svt_encoder* e, const float* wav, int B, int L, void* ws, size_t ws_bytes, float* feats,
                         float* logits, cudaStream_t s) {
@@ -331,7 +423,7 @@ static int forward_impl(svt_encoder* e, const float* wav, int B, int L, void* ws
   __nv_bfloat16* ctx = reinterpret_cast<__nv_bfloat16*>(base + p.off_ctx);
   __nv_bfloat16* mid = reinterpret_cast<__nv_bfloat16*>(base + p.off_mid);
   float* pre = reinterpret_cast<float*>(base + p.off_pre);
-  const int C = c.conv_dim, D = c.hidden_size, H = c.num_heads, dh = D / H;
+  const int C = c.conv_dim, D = c.hidden_size;
   const float eps = c.layer_norm_eps;
 
   // ---- A1 + conv layer 0 (fused input normalisation)
@@ -382,69 +474,13 @@ static int forward_impl(svt_encoder* e, const float* wav, int B, int L, void* ws
     SVT_TRY(layer_norm(ln, s));
     SVT_TRY(linear(cur, M, e->proj, nullptr, h, hb, kActNone, s));
   }
-  // ---- positional conv embedding + residual: h += GELU(conv(h) + b)
-  {
-    GemmArgs g;
-    g.mode = 1;
-    g.a = hb;
-    g.a_dims[0] = D; g.a_dims[1] = T; g.a_dims[2] = B;
-    g.a_strides[0] = D; g.a_strides[1] = static_cast<uint64_t>(Ta) * D;
-    g.w = e->pos_w; g.w_rows = c.pos_conv_groups * c.pos_conv_kernel * 64; g.w_cols = 64;
-    g.N = D; g.K = c.pos_conv_kernel * 64;
-    g.n_clips = B; g.clip_rows = Ta; g.clip_valid = T; g.pad_left = c.pos_conv_kernel / 2; g.taps = c.pos_conv_kernel;
-    g.group_size = D / c.pos_conv_groups;
-    g.bias = e->pos_b; g.resid = h; g.out_f32 = h; g.ld_out = D; g.act = kActGelu;
-    SVT_TRY(gemm_bf16_tc(g, s));
-  }
-  SVT_CUDA(cudaMemsetAsync(ctx, 0, static_cast<size_t>(M) * D * 2, s));  // rows t >= T are never written by attention
-
-  auto ln_rows = [&](const float* x, const NormW& w, __nv_bfloat16* yb, float* yf, double* stats) {
-    LayerNormArgs ln;
-    ln.x_f32 = x; ln.gamma = w.g; ln.beta = w.b; ln.y_bf16 = yb; ln.y_f32 = yf;
-    ln.rows = M; ln.D = D; ln.eps = eps; ln.stats = stats; ln.clip_rows = Ta; ln.clip_valid = T;
-    return layer_norm(ln, s);
-  };
-  auto attend = [&]() {
-    AttentionArgs a;
-    a.q = qkv; a.k = qkv + D; a.v = qkv + 2 * D; a.o = ctx;
-    a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
-    a.Tq = T; a.Tk = T; a.q_clip_rows = Ta; a.k_clip_rows = Ta; a.clips = B; a.heads = H; a.head_dim = dh;
-    return attention_bf16(a, s);
-  };
+  // ---- positional conv + transformer layers (shared with the video stream)
   const bool want_stats = c.output_norm != 0;
-  if (want_stats) SVT_CUDA(cudaMemsetAsync(stats_out, 0, 2 * sizeof(double), s));
   const float* final_x = nullptr;
-
-  if (c.stable_layer_norm) {
-    // pre-LN layers (HF:612-655) + final encoder LN (HF:792)
-    for (int l = 0; l < c.num_layers; ++l) {
-      const svt_encoder::Layer& Lw = e->layers[l];
-      SVT_TRY(ln_rows(h, Lw.ln1, hb, nullptr, nullptr));
-      SVT_TRY(linear(hb, M, Lw.qkv, nullptr, nullptr, qkv, kActNone, s));
-      SVT_TRY(attend());
-      SVT_TRY(linear(ctx, M, Lw.out, h, h, nullptr, kActNone, s));
-      SVT_TRY(ln_rows(h, Lw.ln2, hb, nullptr, nullptr));
-      SVT_TRY(linear(hb, M, Lw.ff1, nullptr, nullptr, mid, kActGelu, s));
-      SVT_TRY(linear(mid, M, Lw.ff2, h, h, nullptr, kActNone, s));
-    }
-    SVT_TRY(ln_rows(h, e->enc_norm, nullptr, pre, want_stats ? stats_out : nullptr));
-    final_x = pre;
-  } else {
-    // post-LN layers (HF:576-609), encoder LN before the stack (HF:692)
-    const bool no_layers = c.num_layers == 0;
-    SVT_TRY(ln_rows(h, e->enc_norm, hb, h, (want_stats && no_layers) ? stats_out : nullptr));
-    for (int l = 0; l < c.num_layers; ++l) {
-      const svt_encoder::Layer& Lw = e->layers[l];
-      const bool last = l == c.num_layers - 1;
-      SVT_TRY(linear(hb, M, Lw.qkv, nullptr, nullptr, qkv, kActNone, s));
-      SVT_TRY(attend());
-      SVT_TRY(linear(ctx, M, Lw.out, h, h, nullptr, kActNone, s));
-      SVT_TRY(ln_rows(h, Lw.ln1, hb, h, nullptr));
-      SVT_TRY(linear(hb, M, Lw.ff1, nullptr, nullptr, mid, kActGelu, s));
-      SVT_TRY(linear(mid, M, Lw.ff2, h, h, nullptr, kActNone, s));
-      SVT_TRY(ln_rows(h, Lw.ln2, hb, h, (want_stats && last) ? stats_out : nullptr));
-    }
-    final_x = h;
+  {
+    TransformerBuffers tb;
+    tb.h = h; tb.hb = hb; tb.qkv = qkv; tb.ctx = ctx; tb.mid = mid; tb.pre = pre;
+    SVT_TRY(encoder_transformer_forward(e, B, T, Ta, tb, want_stats ? stats_out : nullptr, &final_x, s));
   }
   // ---- A7 whole-tensor output norm + head
   HeadArgs ha;
@@ -514,7 +550,7 @@ int svt_encoder_set_head(svt_encoder* enc, const float* w, const float* b, int n
 int svt_encoder_finalize(svt_encoder* enc) {
   if (enc == nullptr) return fail(kInvalidArgument, "null argument");
   if (svt_device_count() <= 0) return fail(kNoDevice, "no CUDA device");
-  return finalize_impl(enc);
+  return encoder_finalize(enc);
 }
 
 int svt_encoder_num_frames(const svt_encoder* enc, int n_samples) {

@@ -18,6 +18,9 @@ struct GemmEpiParams {
   float* out_f32;
   __nv_bfloat16* out_bf16;
   int ld_out, act;
+  const float* alpha;               // kActPRelu slopes
+  const __nv_bfloat16* resid_bf16;  // bf16 residual added BEFORE the activation
+  const uint8_t* row_mask;          // rows with mask 0 are written as zeros
 };
 
 #ifdef __CUDACC__
@@ -67,7 +70,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
                                                    uint32_t tmem_acc, int quad, int half, int lane, uint32_t stage_addr,
                                                    float4 bias4) {
   constexpr int kColsPerWarp = BN / 2;
-  const bool f32_path = (p.out_f32 != nullptr || p.resid != nullptr);
+  const bool f32_path = (p.out_f32 != nullptr || p.resid != nullptr || p.resid_bf16 != nullptr || p.row_mask != nullptr ||
+                         p.act == kActPRelu);
   const int c4 = lane & 7;
   const uint32_t bias_slot = stage_addr + 2048;
   if (!f32_path && p.bias != nullptr) {
@@ -89,8 +93,24 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
       // residual + bias of this chunk in the coalesced mapping (lane = 4 columns of rows 4i + lane / 8), all loads
       // issued before the TMEM read so their latency overlaps it (resid may alias out_f32: loads come first)
       float4 rs[8];
-      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), al = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.bias != nullptr && 4 * c4 < nv) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4 * c4));
+      if (p.act == kActPRelu && 4 * c4 < nv) al = __ldg(reinterpret_cast<const float4*>(p.alpha + col + 4 * c4));
+      uint2 rb[8];
+      uint32_t keep = 0xffu;  // bit i: row 4i + lane / 8 is kept (not a padding-ring row)
+      if (p.resid_bf16 != nullptr || p.row_mask != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3);
+          rb[i] = make_uint2(0u, 0u);
+          if (quad * 32 + rr < valid && 4 * c4 < nv) {
+            const size_t row = static_cast<size_t>(row0 + quad * 32 + rr);
+            if (p.resid_bf16 != nullptr)
+              rb[i] = *reinterpret_cast<const uint2*>(p.resid_bf16 + row * static_cast<size_t>(p.ld_out) + static_cast<size_t>(col + 4 * c4));
+            if (p.row_mask != nullptr && p.row_mask[row] == 0) keep &= ~(1u << i);
+          }
+        }
+      }
       if (p.resid != nullptr) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -121,11 +141,20 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
         const int rr = 4 * i + (lane >> 3);
         float4 a = make_float4(__uint_as_float(raw[i].x) + b4.x, __uint_as_float(raw[i].y) + b4.y,
                                __uint_as_float(raw[i].z) + b4.z, __uint_as_float(raw[i].w) + b4.w);
+        if (p.resid_bf16 != nullptr) {
+          const __nv_bfloat162 r01 = *reinterpret_cast<const __nv_bfloat162*>(&rb[i].x);
+          const __nv_bfloat162 r23 = *reinterpret_cast<const __nv_bfloat162*>(&rb[i].y);
+          a.x += __low2float(r01); a.y += __high2float(r01); a.z += __low2float(r23); a.w += __high2float(r23);
+        }
         if (p.act == kActGelu) {
           a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
         } else if (p.act == kActRelu) {
           a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+        } else if (p.act == kActPRelu) {
+          a.x = a.x > 0.f ? a.x : a.x * al.x; a.y = a.y > 0.f ? a.y : a.y * al.y;
+          a.z = a.z > 0.f ? a.z : a.z * al.z; a.w = a.w > 0.f ? a.w : a.w * al.w;
         }
+        if (!((keep >> i) & 1u)) a = make_float4(0.f, 0.f, 0.f, 0.f);
         if (quad * 32 + rr < valid && 4 * c4 < nv) {
           const size_t off = static_cast<size_t>(row0 + quad * 32 + rr) * static_cast<size_t>(p.ld_out) +
                              static_cast<size_t>(col + 4 * c4);

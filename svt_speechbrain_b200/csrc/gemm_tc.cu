@@ -37,6 +37,8 @@ struct KParams {
   int tiles_per_clip, clip_rows, clip_valid, pad_left;
   int n_stride;  // output-column (and posconv input-channel) offset per n-tile
   int n_valid;   // valid output columns per n-tile (<= BN)
+  int n_taps, kb_per_tap;  // shifted-row taps (0: off)
+  int tap_off[kMaxGemmTaps];
   GemmEpiParams e;
 };
 
@@ -99,7 +101,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* sb = sa + C::kABytes;
         if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-          if (p.mode == 0) {
+          if (p.mode == 0 && p.n_taps > 0) {
+            // implicit 2-D conv over flat padded rows: tap = constant row shift, OOB rows read as zero
+            const int tap = kb / p.kb_per_tap;
+            tma_load_3d(sa, &tmA, &full_bar[stage], (kb % p.kb_per_tap) * BK, 0, m_tile * BM + p.tap_off[tap]);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_tile * BN);
+          } else if (p.mode == 0) {
             const int k0 = kb * BK;
             tma_load_3d(sa, &tmA, &full_bar[stage], k0 % p.k_inner, k0 / p.k_inner, m_tile * BM);
             tma_load_2d(sb, &tmB, &full_bar[stage], k0, n_tile * BN);
@@ -281,7 +288,7 @@ int launch(const GemmArgs& g, const KParams& kp, cudaStream_t stream) {
 }  // namespace
 
 int gemm_bf16_tc(const GemmArgs& g, cudaStream_t stream) {
-  if (get_option_gemm_impl() != 1 && gemm_pair_supported(g) && g.M >= 1024) return gemm_bf16_tc_pair(g, stream);
+  if (get_option_gemm_impl() != 1 && gemm_pair_supported(g) && g.M >= 1024 && g.n_taps == 0) return gemm_bf16_tc_pair(g, stream);
   KParams kp{};
   kp.mode = g.mode;
   kp.M = g.M;
@@ -295,6 +302,18 @@ int gemm_bf16_tc(const GemmArgs& g, cudaStream_t stream) {
   kp.e.out_bf16 = g.out_bf16;
   kp.e.ld_out = g.ld_out;
   kp.e.act = g.act;
+  kp.e.alpha = g.alpha;
+  kp.e.resid_bf16 = g.resid_bf16;
+  kp.e.row_mask = g.row_mask;
+  if (g.act == kActPRelu && g.alpha == nullptr) return fail(kInvalidArgument, "gemm: PReLU needs per-column slopes");
+  kp.n_taps = 0;
+  if (g.n_taps > 0) {
+    if (g.mode != 0 || g.n_taps > kMaxGemmTaps || kp.k_inner % BK != 0 || g.K != g.n_taps * kp.k_inner)
+      return fail(kInvalidArgument, "gemm: bad tap configuration");
+    kp.n_taps = g.n_taps;
+    kp.kb_per_tap = kp.k_inner / BK;
+    for (int i = 0; i < g.n_taps; ++i) kp.tap_off[i] = g.tap_off[i];
+  }
   if (g.mode == 0 && (g.K % BK != 0 || kp.k_inner % BK != 0))
     return fail(kInvalidArgument, "gemm: K must be a multiple of 64");
   if (g.ld_out % 8 != 0) return fail(kInvalidArgument, "gemm: ld_out must be a multiple of 8");

@@ -5,7 +5,8 @@
 
 namespace svt {
 
-enum GemmAct : int { kActNone = 0, kActGelu = 1, kActRelu = 2 };
+enum GemmAct : int { kActNone = 0, kActGelu = 1, kActRelu = 2, kActPRelu = 3 };
+constexpr int kMaxGemmTaps = 9;
 
 // C[row, n] = act( sum_k A[row, k] * W[n, k] + bias[n] ) (+ resid[row, n])
 //
@@ -41,6 +42,14 @@ struct GemmArgs {
   __nv_bfloat16* out_bf16 = nullptr;
   int ld_out = 0;                          // leading dimension (elements) of out_f32 / out_bf16 / resid
   int act = kActNone;
+  const float* alpha = nullptr;            // [N] per-column slope for kActPRelu
+  const __nv_bfloat16* resid_bf16 = nullptr;  // bf16 residual [rows, ld_out] added before the activation (ResNet blocks)
+  const uint8_t* row_mask = nullptr;       // [rows]: rows with mask 0 are written as zeros (padding ring of a feature map)
+  // ---- shifted-row taps (linear mode only): k-block kb reads A rows (row + tap_off[kb / (k_inner / 64)]), columns
+  // (kb % (k_inner / 64)) * 64 .. + 64; K = n_taps * k_inner.  This is a 2-D convolution over feature maps stored as
+  // flat rows [frame][y][x] with a zero padding ring: tap (dy, dx) is the constant row offset dy * W_padded + dx.
+  int n_taps = 0;
+  int tap_off[kMaxGemmTaps] = {0};
   // optional second bf16 output written transposed per clip is not needed (attention reads row-major V)
 };
 

@@ -245,7 +245,7 @@ int gemm_bf16_tc_pair(const GemmArgs& g, cudaStream_t stream) {
   if (g.ld_out % 8 != 0) return fail(kInvalidArgument, "gemm: ld_out must be a multiple of 8");
   GemmEpiParams p{};
   p.M = g.M; p.bias = g.bias; p.resid = g.resid; p.out_f32 = g.out_f32; p.out_bf16 = g.out_bf16;
-  p.ld_out = g.ld_out; p.act = g.act;
+  p.ld_out = g.ld_out; p.act = g.act; p.alpha = g.alpha; p.resid_bf16 = g.resid_bf16; p.row_mask = g.row_mask;
   const int k_inner = g.k_inner > 0 ? g.k_inner : g.K;
   CUtensorMap tmA, tmB;
   const uint32_t abox[3] = {BK, 1, BM};

@@ -65,6 +65,19 @@ int pack_posconv_weight(const float* w_dev, const float* tap_scale, int D, int g
                         cudaStream_t stream);
 }
 
+namespace svt {
+// scratch of the shared transformer body (rows M = clips * Ta): h fp32 [M, D] residual stream (in / out), hb bf16 copy
+// [M, D] (in), qkv bf16 [M, 3D], ctx bf16 [M, D], mid bf16 [M, F], pre fp32 [M, D]
+struct TransformerBuffers {
+  float* h = nullptr;
+  __nv_bfloat16* hb = nullptr;
+  __nv_bfloat16* qkv = nullptr;
+  __nv_bfloat16* ctx = nullptr;
+  __nv_bfloat16* mid = nullptr;
+  float* pre = nullptr;
+};
+}  // namespace svt
+
 struct svt_encoder {
   ~svt_encoder() {
     if (head_w != nullptr) cudaFree(head_w);
@@ -74,6 +87,7 @@ struct svt_encoder {
   svt::WeightRegistry reg;
   svt::DevicePool pool;
   bool finalized = false;
+  bool transformer_only = false;  // AV-HuBERT video stream: only the positional conv + layers are packed
 
   // packed weights
   float* conv0_w = nullptr;  // [k][C] fp32
@@ -99,6 +113,12 @@ struct svt_encoder {
   int conv_out_len(int L, int upto) const;  // valid frames after conv layers 0..upto
   int t_alloc0(int L) const;                // allocated frames of layer 0 (multiple of prod(strides[1:]) and 4)
 };
+
+namespace svt {
+int encoder_finalize(svt_encoder* e);
+int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, const TransformerBuffers& tb, double* stats_out,
+                                const float** final_x_out, cudaStream_t s);
+}  // namespace svt
 
 struct svt_fusion {
   svt_fusion_config cfg{};

@@ -7,7 +7,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from ._lib import EncoderConfig, FusionConfig, check, current_stream_ptr, lib, ptr, require_cuda
+from ._lib import EncoderConfig, FusionConfig, VideoConfig, check, current_stream_ptr, lib, ptr, require_cuda
 
 
 def encoder_config_from_hf(cfg, normalize_wav: bool, output_norm: bool) -> EncoderConfig:
@@ -168,6 +168,50 @@ class FusionEngine:
         try:
             if self._h:
                 lib().svt_fusion_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
+class VideoEngine:
+    """svt_video handle (AV-HuBERT video stream) + cached workspace."""
+
+    def __init__(self, cfg: VideoConfig, device):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("VideoEngine needs a CUDA device (no CPU fallback)")
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().svt_video_create(C.byref(cfg), C.byref(self._h)))
+        self._ws = None
+
+    def load(self, state_dict):
+        with torch.cuda.device(self.device):
+            _set_tensors(lib().svt_video_set_tensor, self._h, state_dict)
+            check(lib().svt_video_finalize(self._h))
+
+    def forward(self, video: torch.Tensor) -> torch.Tensor:
+        """video (B, 1, T, 88, 88) CUDA fp32 -> (B, T, D) fp32"""
+        require_cuda(video, "VideoEngine.forward")
+        if video.dim() != 5 or video.shape[1] != 1 or tuple(video.shape[3:]) != (88, 88):
+            raise ValueError(f"expected video of shape (B, 1, T, 88, 88), got {tuple(video.shape)}")
+        video = video.to(torch.float32).contiguous()
+        B, _, T, _, _ = video.shape
+        need = lib().svt_video_workspace_bytes(self._h, B, T)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        out = torch.empty(B, T, self.cfg.embed_dim, dtype=torch.float32, device=video.device)
+        with torch.cuda.device(video.device):
+            check(lib().svt_video_forward(self._h, ptr(video), B, T, ptr(self._ws), self._ws.numel(), ptr(out),
+                                          current_stream_ptr()))
+        return out
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().svt_video_destroy(self._h)
                 self._h = C.c_void_p()
         except Exception:
             pass

@@ -1,0 +1,97 @@
+"""AV-HuBERT video stream (csrc/video.cu) vs the CPU oracle (oracle/avhubert_oracle.py, whose ResNet front end is
+pinned to the reference's resnet.py) through the C ABI / the FairseqAVHubertPretrain drop-in."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def _lobe(cfg, sd, output_norm=True, input_norm=None):
+    from svt_speechbrain_b200.fairseq_interface import FairseqAVHubertPretrain
+    mc = dict(encoder_embed_dim=cfg.encoder_embed_dim, encoder_layers=cfg.encoder_layers,
+              encoder_attention_heads=cfg.encoder_attention_heads, encoder_ffn_embed_dim=cfg.encoder_ffn_embed_dim,
+              conv_pos=cfg.conv_pos, conv_pos_groups=cfg.conv_pos_groups)
+    lobe = FairseqAVHubertPretrain(None, None, input_norm=input_norm, output_norm=output_norm, pretrain=False, model_config=mc)
+    own = lobe.state_dict()
+    new = {k: sd[k] for k in own if k in sd}
+    missing = [k for k in own if k not in new and "num_batches_tracked" not in k and "feature_extractor_audio" not in k
+               and not k.endswith("mask_emb")]
+    assert not missing, missing[:5]
+    lobe.load_state_dict(new, strict=False)
+    return lobe
+
+
+def test_resnet_front_end_vs_reference_golden():
+    """Zero transformer layers and identity glue: the stream reduces to ResEncoder -> proj; compare with the reference's own
+    resnet.ResEncoder output (golden) pushed through the same proj / LN / post-proj on the CPU."""
+    from oracle import avhubert_oracle as av
+    d = np.load(os.path.join(GOLD, "avhubert_resnet_b2_t6.npz"))
+    cfg = av.AVHubertConfig(encoder_embed_dim=256, encoder_layers=0, encoder_attention_heads=4, encoder_ffn_embed_dim=512,
+                            conv_pos=16, conv_pos_groups=4)
+    sd = av.random_weights(cfg, seed=int(d["weight_seed"]))
+    g = torch.Generator().manual_seed(int(d["video_seed"]))
+    video = torch.randn(int(d["B"]), 1, int(d["T"]), 88, 88, generator=g)
+    taps = {}
+    with torch.no_grad():
+        ref = av.lobe_forward(cfg, sd, video, output_norm=False, taps=taps)
+    # the oracle's front end is the golden (bit-exact on CPU): check that first, then the CUDA path against the oracle
+    res = av.res_encoder(sd, video, "model.feature_extractor_video.resnet.")
+    assert float((res - torch.from_numpy(d["out"])).abs().max()) < 1e-4
+    got = _lobe(cfg, sd, output_norm=False)({"video": video.cuda(), "audio": None}).cpu()
+    print(f"video stream (0 layers): max-abs {float((got - ref).abs().max()):.3e} rel-L2 {_rel(got, ref):.3e}")
+    assert got.shape == ref.shape == (2, 6, 256)
+    assert _rel(got, ref) < 2e-2
+
+
+@pytest.mark.parametrize("T,B,input_norm", [(7, 2, False), (12, 1, True)])
+def test_video_stream_small_transformer_vs_oracle(T, B, input_norm):
+    from oracle import avhubert_oracle as av
+    cfg = av.AVHubertConfig(encoder_embed_dim=256, encoder_layers=2, encoder_attention_heads=4, encoder_ffn_embed_dim=512,
+                            conv_pos=32, conv_pos_groups=4)
+    sd = av.random_weights(cfg, seed=3)
+    video = torch.randn(B, 1, T, 88, 88, generator=torch.Generator().manual_seed(T))
+    with torch.no_grad():
+        ref = av.lobe_forward(cfg, sd, video, input_norm=input_norm, output_norm=True)
+    got = _lobe(cfg, sd, output_norm=True, input_norm=input_norm)({"video": video.cuda(), "audio": None}).cpu()
+    print(f"video stream T={T} B={B}: max-abs {float((got - ref).abs().max()):.3e} rel-L2 {_rel(got, ref):.3e}")
+    assert torch.isfinite(got).all()
+    assert _rel(got, ref) < 2e-2 and float((got - ref).abs().max()) < 0.15
+
+
+def test_video_stream_large_config_short_clip():
+    """AV-HuBERT-large geometry (24 x 1024 / 4096 / 16 heads), 1 s of video."""
+    from oracle import avhubert_oracle as av
+    cfg = av.AVHubertConfig()
+    sd = av.random_weights(cfg, seed=0)
+    video = torch.randn(1, 1, 50, 88, 88, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        ref = av.lobe_forward(cfg, sd, video)
+    got = _lobe(cfg, sd)({"video": video.cuda(), "audio": None}).cpu()
+    print(f"video stream large T=50: max-abs {float((got - ref).abs().max()):.3e} rel-L2 {_rel(got, ref):.3e}")
+    assert _rel(got, ref) < 2e-2
+
+
+def test_state_dict_keys_follow_the_reference_names():
+    from svt_speechbrain_b200.fairseq_interface import FairseqAVHubertPretrain
+    lobe = FairseqAVHubertPretrain(None, None, pretrain=False,
+                                   model_config=dict(encoder_embed_dim=256, encoder_layers=1, encoder_attention_heads=4,
+                                                     encoder_ffn_embed_dim=512, conv_pos=16, conv_pos_groups=4))
+    keys = set(lobe.state_dict())
+    for k in ("model.feature_extractor_video.resnet.frontend3D.0.weight", "model.feature_extractor_video.resnet.frontend3D.1.running_var",
+              "model.feature_extractor_video.resnet.trunk.layer2.0.downsample.0.weight",
+              "model.feature_extractor_video.resnet.trunk.layer4.1.relu2.weight", "model.feature_extractor_video.proj.weight",
+              "model.feature_extractor_audio.proj.bias", "model.layer_norm.weight", "model.post_extract_proj.weight",
+              "model.mask_emb", "model.encoder.pos_conv.0.weight_g", "model.encoder.pos_conv.0.weight_v", "model.encoder.pos_conv.0.bias",
+              "model.encoder.layers.0.self_attn.q_proj.weight", "model.encoder.layers.0.self_attn_layer_norm.bias",
+              "model.encoder.layers.0.fc1.weight", "model.encoder.layers.0.final_layer_norm.weight", "model.encoder.layer_norm.weight"):
+        assert k in keys, k
+    with pytest.raises(RuntimeError):
+        lobe({"video": torch.zeros(1, 1, 4, 88, 88), "audio": None})

@@ -3,7 +3,7 @@
 # usage: tools/run_gpu_checks.sh [files...]
 mkdir -p gpurun_out
 files=("$@")
-if [ ${#files[@]} -eq 0 ]; then files=(tests/test_gpu_gemm.py tests/test_gpu_gemm_pair.py tests/test_gpu_attention_tc.py tests/test_gpu_ops.py tests/test_gpu_e2e.py); fi
+if [ ${#files[@]} -eq 0 ]; then files=(tests/test_gpu_gemm.py tests/test_gpu_gemm_pair.py tests/test_gpu_attention_tc.py tests/test_gpu_ops.py tests/test_gpu_video.py tests/test_gpu_e2e.py); fi
 nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 rc=0
 for f in "${files[@]}"; do

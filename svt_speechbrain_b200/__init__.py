@@ -4,15 +4,17 @@ Reference-shaped modules (same names, constructor kwargs, forward signatures and
     HuggingFaceWav2Vec2  <- MIR_ST500/huggingface_interface.py
     Linear               <- speechbrain/nnet/linear.py
     FusionRCA            <- N20EMv2/audio_visual/fusion.py
+    FairseqAVHubertPretrain <- N20EMv2/video_only/fairseq_interface.py
     frame2note           <- MIR_ST500/utils.py
 All arithmetic runs in the C-ABI library libsvt_b200.so (include/svt_b200.h); there is no CPU fallback.
 """
 from ._lib import LIB_PATH, SvtError, lib  # noqa: F401
-from .amt import AMTHparams, AMTTranscriber, split_song  # noqa: F401
+from .amt import AMTHparams, AMTTranscriber, AVTranscriber, split_song  # noqa: F401
+from .fairseq_interface import FairseqAVHubertPretrain  # noqa: F401
 from .fusion import FusionRCA  # noqa: F401
 from .huggingface_interface import HuggingFaceWav2Vec2  # noqa: F401
 from .linear import Linear  # noqa: F401
 from .utils import decode_arrays, frame2note  # noqa: F401
 
-__all__ = ["HuggingFaceWav2Vec2", "Linear", "FusionRCA", "frame2note", "decode_arrays", "AMTTranscriber", "AMTHparams",
+__all__ = ["HuggingFaceWav2Vec2", "FairseqAVHubertPretrain", "AVTranscriber", "Linear", "FusionRCA", "frame2note", "decode_arrays", "AMTTranscriber", "AMTHparams",
            "split_song", "lib", "SvtError", "LIB_PATH"]

@@ -121,3 +121,28 @@ class AMTTranscriber:
                 pieces.extend(lg[k] for k in range(lg.shape[0]))
                 i = j
         return self.decode(torch.cat(pieces, dim=0))
+
+
+class AVTranscriber:
+    """Online audio-visual AMT (BASELINE config 4): the reference does this in three offline stages with cached features
+    (N20EMv2/audio_only/extract_ssl_feats.py, video_only/extract_ssl_feats.py, audio_visual/train_rca_av.py:28-51); here
+    wav -> audio lobe, lip video -> video lobe, FusionRCA, Linear head and the decoder run back to back on one GPU.
+
+    audio_lobe: HuggingFaceWav2Vec2, video_lobe: FairseqAVHubertPretrain, fusion: FusionRCA, head: Linear (20 outputs)."""
+
+    def __init__(self, audio_lobe, video_lobe, fusion, head, hparams: Optional[AMTHparams] = None, device="cuda"):
+        self.audio_lobe, self.video_lobe, self.fusion, self.head = audio_lobe, video_lobe, fusion, head
+        self.hp = hparams or AMTHparams()
+        self.device = torch.device(device)
+        self._decoder = AMTTranscriber.__new__(AMTTranscriber)
+        self._decoder.hp = self.hp
+
+    @torch.no_grad()
+    def logits(self, wav: torch.Tensor, video: torch.Tensor) -> torch.Tensor:
+        """wav (B, L), video (B, 1, T, 88, 88) on CUDA -> frame logits (B, T_audio, 20)  (train_rca_av.py:38-49)."""
+        a = self.audio_lobe(wav)
+        v = self.video_lobe({"video": video, "audio": None})
+        return self.head(self.fusion(a, v))
+
+    def decode(self, logits: torch.Tensor) -> np.ndarray:
+        return self._decoder.decode(logits)

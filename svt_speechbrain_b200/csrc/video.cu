@@ -49,17 +49,21 @@ struct ConvW {
 // Patch matrix of the Conv3d front end: row (n, y, x) = frame slot n = b * Ta + t, output pixel (y, x) of 44 x 44;
 // column k = (dt * 7 + dy) * 7 + dx < 245 holds video[b, t + dt - 2, 2y + dy - 3, 2x + dx - 3] (zero outside the
 // clip / image), optionally whole-tensor normalised first; columns 245..255 and frame slots t >= T are zero.
+// One CTA = one output row y of one frame slot: the 5 x 7 input rows it touches are staged in shared memory
+// (coalesced 352-byte row loads), then each warp emits whole 512-byte patch rows.
 __global__ void __launch_bounds__(256) frontend_im2col_kernel(const float* __restrict__ video, int B, int T, int Ta,
                                                               const double* __restrict__ in_stats, double inv_count,
                                                               __nv_bfloat16* __restrict__ col) {
-  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  const long long n_rows = static_cast<long long>(B) * Ta * kF0 * kF0;
-  if (row >= n_rows) return;
-  const int lane = threadIdx.x & 31;
-  const int x = static_cast<int>(row % kF0);
-  const int y = static_cast<int>((row / kF0) % kF0);
-  const int n = static_cast<int>(row / (kF0 * kF0));
+  __shared__ float tile[5][7][kImg];
+  const int y = blockIdx.x % kF0;
+  const int n = blockIdx.x / kF0;
   const int t = n % Ta, b = n / Ta;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __nv_bfloat16* out = col + (static_cast<size_t>(n) * kF0 + y) * kF0 * kFrontK;
+  if (t >= T) {  // padding frame slot: all-zero patches
+    for (int i = threadIdx.x; i < kF0 * kFrontK / 8; i += 256) reinterpret_cast<uint4*>(out)[i] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
   float mean = 0.f, rstd = 1.f;
   if (in_stats != nullptr) {
     const double m = in_stats[0] * inv_count;
@@ -67,21 +71,33 @@ __global__ void __launch_bounds__(256) frontend_im2col_kernel(const float* __res
     mean = static_cast<float>(m);
     rstd = static_cast<float>(1.0 / sqrt((var > 0 ? var : 0) + 1e-5));
   }
-  float v[8];
+  for (int i = threadIdx.x; i < 5 * 7 * kImg; i += 256) {
+    const int xi = i % kImg, dy = (i / kImg) % 7, dt = i / (7 * kImg);
+    const int ti = t + dt - 2, yi = 2 * y + dy - 3;
+    float v = 0.f;  // zero padding of the (normalised) input
+    if (ti >= 0 && ti < T && yi >= 0 && yi < kImg) v = (__ldg(video + ((static_cast<size_t>(b) * T + ti) * kImg + yi) * kImg + xi) - mean) * rstd;
+    tile[dt][dy][xi] = v;
+  }
+  __syncthreads();
+  int off[8], dxs[8];  // this lane's 8 patch columns: offset of (dt, dy) in the tile and dx
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int k = lane * 8 + i;
-    float val = 0.f;
-    if (k < 245 && t < T) {
-      const int dx = k % 7, dy = (k / 7) % 7, dt = k / 49;
-      const int ti = t + dt - 2, yi = 2 * y + dy - 3, xi = 2 * x + dx - 3;
-      if (ti >= 0 && ti < T && yi >= 0 && yi < kImg && xi >= 0 && xi < kImg)
-        val = (__ldg(video + ((static_cast<size_t>(b) * T + ti) * kImg + yi) * kImg + xi) - mean) * rstd;
-    }
-    v[i] = val;
+    const int dx = k % 7, dy = (k / 7) % 7, dt = k / 49;
+    off[i] = k < 245 ? (dt * 7 + dy) * kImg : -1;
+    dxs[i] = dx - 3;
   }
-  *reinterpret_cast<uint4*>(col + row * kFrontK + lane * 8) =
-      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  const float* flat = &tile[0][0][0];
+  for (int x = warp; x < kF0; x += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int xi = 2 * x + dxs[i];
+      v[i] = (off[i] >= 0 && xi >= 0 && xi < kImg) ? flat[off[i] + xi] : 0.f;
+    }
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(x) * kFrontK + lane * 8) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
 }
 
 // MaxPool3d((1,3,3), stride (1,2,2), pad (0,1,1)): [N][44][44][64] -> padded [N][24][24][64] (ring = 0)
@@ -367,7 +383,7 @@ int forward_video(svt_video* v, const float* video, int B, int T, void* ws, size
   // ---- Conv3d front end as patch matrix + GEMM (BN folded, PReLU epilogue)
   {
     const long long rows = static_cast<long long>(N) * kF0 * kF0;
-    frontend_im2col_kernel<<<grid_for(rows, 8), 256, 0, s>>>(video, B, T, Ta, v->cfg.input_norm ? stats_in : nullptr,
+    frontend_im2col_kernel<<<N * kF0, 256, 0, s>>>(video, B, T, Ta, v->cfg.input_norm ? stats_in : nullptr,
                                                              1.0 / (static_cast<double>(B) * T * kImg * kImg), col);
     SVT_POST_LAUNCH();
     SVT_TRY(conv_gemm(v->front, col, rows, 0, nullptr, nullptr, true, f0, s));

@@ -95,3 +95,47 @@ def test_state_dict_keys_follow_the_reference_names():
         assert k in keys, k
     with pytest.raises(RuntimeError):
         lobe({"video": torch.zeros(1, 1, 4, 88, 88), "audio": None})
+
+
+def test_audio_visual_pipeline_vs_composed_oracle():
+    """BASELINE config 4 in miniature: wav2vec2-large (1 s) + AV-HuBERT-large (50 frames) + FusionRCA + Linear head on the GPU
+    against the same composition of the CPU oracles; notes decoded from the GPU logits equal the oracle decoder's."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import svt_speechbrain_b200 as svt
+    from oracle import avhubert_oracle as av
+    from oracle import fusion_oracle as fo
+    from oracle import make_golden as mg
+    from oracle import wav2vec2_oracle as wo
+    from oracle.frame2note_oracle import frame2note as f2n_oracle
+    from test_gpu_e2e import _build
+
+    wcfg = wo.W2V2Config.large()
+    alobe, lin, asd, head = _build(wcfg)
+    vcfg = av.AVHubertConfig()
+    vsd = av.random_weights(vcfg, seed=0)
+    vlobe = _lobe(vcfg, vsd)
+    fsd = mg.random_fusion_weights(1024, 3072, seed=3)
+    fus = svt.FusionRCA()
+    full = dict(fus.state_dict())
+    full.update(fsd)
+    fus.load_state_dict(full, strict=True)
+    fus = fus.cuda()
+    g = torch.Generator().manual_seed(21)
+    wav = torch.randn(2, 16000, generator=g)
+    video = torch.randn(2, 1, 50, 88, 88, generator=g)
+    with torch.no_grad():
+        a = wo.lobe_forward(wcfg, asd, wav)
+        v = av.lobe_forward(vcfg, vsd, video)
+        ref = wo.head_forward(head, fo.fusion_forward(fsd, a, v))
+    tr = svt.AVTranscriber(alobe, vlobe, fus, lin)
+    got = tr.logits(wav.cuda(), video.cuda())
+    rel = _rel(got.cpu(), ref)
+    print(f"AV pipeline logits: max-abs {float((got.cpu() - ref).abs().max()):.3e} rel-L2 {rel:.3e}")
+    assert got.shape == ref.shape == (2, 49, 20)
+    assert rel < 2e-2
+    notes = tr.decode(got[0])
+    p_on, p_off, octv, pc = wo.frame_info_from_logits(got[0].cpu())
+    fi = [(p_on[i], p_off[i], int(octv[i]), int(pc[i])) for i in range(len(p_on))]
+    want = np.array(f2n_oracle(fi, 0.4, 0.5, 1 / 49.8), dtype=np.float64).reshape(-1, 3)
+    assert notes.shape == want.shape and np.array_equal(notes, want)

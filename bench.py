@@ -23,8 +23,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GFLOP_PER_AUDIO_SEC = 38.386  # BASELINE.md section 3 (wav2vec2-large, 10-s clips, 2*MAC)
+FFN1_DRAM_BYTES = None  # filled below from the committed ncu capture of the roofline kernel
 CLIP_SECONDS = 10
 SAMPLE_RATE = 16000
+
+
+def _ffn1_traffic():
+    """DRAM bytes of one launch of the roofline kernel, from the committed `ncu --set full` capture summary."""
+    import csv
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_v2_summary.csv")) as f:
+            rows = list(csv.reader(f))
+        h = rows[0]
+        for r in rows[1:]:
+            d = dict(zip(h, r))
+            if "gemm_tc2" in d.get("Kernel Name", ""):
+                return int((float(d["dram__bytes_read.sum [Mbyte]"]) + float(d["dram__bytes_write.sum [Mbyte]"])) * 1e6)
+    except Exception:
+        pass
+    return None
+
+
+FFN1_DRAM_BYTES = _ffn1_traffic()
 
 
 def _peaks():
@@ -261,8 +281,10 @@ def run_ours(args):
         t_ms = sum(times) / len(times)
         tf = 2.0 * M * N * K / (t_ms * 1e-3) / 1e12
         step_tf = GFLOP_PER_AUDIO_SEC * 1e9 * (value / world) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<256> (FFN-1 shape M=%d N=%d K=%d, bias+GELU epilogue)" % (M, N, K),
-                "achieved": tf, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": tf / peaks["bf16"], "traffic": None,
+        roof = {"bound": "tensor", "kernel": "gemm_tc2_kernel, CTA-pair tcgen05 GEMM (FFN-1 shape M=%d N=%d K=%d, bias+GELU epilogue)" % (M, N, K),
+                "achieved": tf, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": tf / peaks["bf16"], "traffic": FFN1_DRAM_BYTES,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full, "
+                                  "profiles/r1_ncu_full_v2_summary.csv (algorithmic: A 65.5 MB + W 8.4 MB + out 262.1 MB)",
                 "peak_source": peaks["src"] + " burst (kernel timed alone)", "us_per_launch": t_ms * 1e3,
                 "whole_step": {"achieved": step_tf, "peak": peaks["bf16_sustained"], "frac": step_tf / peaks["bf16_sustained"],
                                "peak_source": peaks["src"] + " sustained", "note": "38.386 GFLOP per audio-second (BASELINE.md section 3)"}}

@@ -42,6 +42,80 @@ struct KParams {
   GemmEpiParams e;
 };
 
+// Epilogue of the tap-paired positional conv.  The accumulator holds D'[r][s * 64 + co] = sum over k-blocks of
+// x[t0 + r + 4kb - pad, :] . W_{4kb + s}[co, :] for r < 128, s < 4, so the conv output of frame t0 + r' is
+// sum_s D'[r' + s][s * 64 + co]: every 128-row tile yields kPosRows = 125 frames.  The four column blocks are added
+// into a [128][64] fp32 tile in shared memory with a row shift of s (phase s; named barriers between phases because
+// shifted rows cross the warps' lane quadrants), then all 8 warps read it back as whole 256-byte rows and apply
+// bias + GELU + the fp32 residual.  acc tile = the 32 KB staging area; 16-byte slots XOR-swizzled by (row & 7).
+constexpr int kPosRows = 125;
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void posconv_epilogue_tile(const GemmEpiParams& p, int row0, int valid, int col0, int n_valid,
+                                                      uint32_t tmem_acc, int quad, int half, int lane, uint32_t acc_addr,
+                                                      uint64_t* tempty) {
+  const int r = quad * 32 + lane;  // accumulator row of this thread
+  const uint32_t tmem_row = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+  for (int s = 0; s < 4; ++s) {
+    if ((s >> 1) == half) {
+      const int dst = r - s;  // output row this block contributes to
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_row + static_cast<uint32_t>(s * 64 + c), v);
+        tmem_ld_wait();
+        if (dst >= 0) {
+          const uint32_t row_addr = acc_addr + dst * 256;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t a = row_addr + ((((c >> 2) + q) ^ (dst & 7)) << 4);
+            if (s == 0) {
+              epi_sts128(a, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+              const uint4 o = epi_lds128(a);
+              epi_sts128(a, __float_as_uint(__uint_as_float(o.x) + __uint_as_float(v[4 * q])),
+                         __float_as_uint(__uint_as_float(o.y) + __uint_as_float(v[4 * q + 1])),
+                         __float_as_uint(__uint_as_float(o.z) + __uint_as_float(v[4 * q + 2])),
+                         __float_as_uint(__uint_as_float(o.w) + __uint_as_float(v[4 * q + 3])));
+            }
+          }
+        }
+      }
+      if ((s & 1) == 1) {  // this warp's last TMEM read of the tile: release the accumulator stage
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty);
+      }
+    }
+    epi_bar_sync();
+  }
+  // read back: warp w = 4 * half + quad owns rows 16w .. 16w + 15, two rows per instruction (16 lanes x float4 each)
+  const int w = half * 4 + quad;
+  const int slot = lane & 15;
+  const int ncol = 4 * slot;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias != nullptr && ncol < n_valid) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + ncol));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = 16 * w + 2 * i + (lane >> 4);
+    const uint4 o = epi_lds128(acc_addr + rr * 256 + ((slot ^ (rr & 7)) << 4));
+    if (rr < kPosRows && rr < valid && ncol < n_valid) {
+      float4 a = make_float4(__uint_as_float(o.x) + b4.x, __uint_as_float(o.y) + b4.y, __uint_as_float(o.z) + b4.z,
+                             __uint_as_float(o.w) + b4.w);
+      if (p.act == kActGelu) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+      const size_t off = static_cast<size_t>(row0 + rr) * static_cast<size_t>(p.ld_out) + static_cast<size_t>(col0 + ncol);
+      if (p.resid != nullptr) {
+        const float4 q = *reinterpret_cast<const float4*>(p.resid + off);
+        a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+      }
+      if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + off) = a;
+      if (p.out_bf16 != nullptr) *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+    }
+  }
+  epi_bar_sync();  // the next tile's phase 0 overwrites the acc tile
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
@@ -110,9 +184,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int k0 = kb * BK;
             tma_load_3d(sa, &tmA, &full_bar[stage], k0 % p.k_inner, k0 / p.k_inner, m_tile * BM);
             tma_load_2d(sb, &tmB, &full_bar[stage], k0, n_tile * BN);
-          } else {
+          } else if (p.mode == 1) {
             // positional conv: group = n_tile, tap = kb; frames shifted by (tap - pad_left), OOB -> 0
             tma_load_3d(sa, &tmA, &full_bar[stage], n_tile * p.n_stride, tt * BM + kb - p.pad_left, clip);
+            tma_load_2d(sb, &tmB, &full_bar[stage], 0, (n_tile * p.num_kb + kb) * BN);
+          } else {
+            // tap-paired positional conv: k-block kb = taps 4kb .. 4kb+3 as 4 x 64 accumulator columns against ONE
+            // A tile shifted by (4kb - pad_left); the tile yields kPosRows output frames (see posconv_epilogue_tile)
+            tma_load_3d(sa, &tmA, &full_bar[stage], n_tile * p.n_stride, tt * kPosRows + 4 * kb - p.pad_left, clip);
             tma_load_2d(sb, &tmB, &full_bar[stage], 0, (n_tile * p.num_kb + kb) * BN);
           }
         }
@@ -188,18 +267,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int nn = nt % p.n_tiles, nm = nt / p.n_tiles;
           int nrow0, nvalid;
           if (p.mode == 0) { nrow0 = nm * BM; nvalid = p.M - nrow0; }
-          else { const int cl = nm / p.tiles_per_clip, tt = nm % p.tiles_per_clip; nrow0 = cl * p.clip_rows + tt * BM; nvalid = p.clip_valid - tt * BM; }
+          else { const int cl = nm / p.tiles_per_clip, tt = nm % p.tiles_per_clip, step = p.mode == 2 ? kPosRows : BM;
+                 nrow0 = cl * p.clip_rows + tt * step; nvalid = p.clip_valid - tt * step; }
           gemm_prefetch_resid<BN>(p.e, nrow0, nvalid, nn * p.n_stride, p.n_valid);
         }
       }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      gemm_epilogue_tile<BN>(p.e, row0, valid, n_tile * p.n_stride, p.n_valid, tmem_base + static_cast<uint32_t>(as * BN), quad,
-                             half, lane, stage_mine, bias_cur);
-      // all of this warp's TMEM reads are complete (wait::ld above) -> release the accumulator stage
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (BN == 256 && p.mode == 2) {
+        const int clip = m_tile / p.tiles_per_clip;
+        const int tt = m_tile % p.tiles_per_clip;
+        posconv_epilogue_tile(p.e, clip * p.clip_rows + tt * kPosRows, p.clip_valid - tt * kPosRows, n_tile * p.n_stride, p.n_valid,
+                              tmem_base + static_cast<uint32_t>(as * BN), quad, half, lane, smem_u32(stage_area), &tempty_bar[as]);
+      } else {
+        gemm_epilogue_tile<BN>(p.e, row0, valid, n_tile * p.n_stride, p.n_valid, tmem_base + static_cast<uint32_t>(as * BN), quad,
+                               half, lane, stage_mine, bias_cur);
+        // all of this warp's TMEM reads are complete (wait::ld above) -> release the accumulator stage
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
@@ -318,7 +405,22 @@ int gemm_bf16_tc(const GemmArgs& g, cudaStream_t stream) {
     return fail(kInvalidArgument, "gemm: K must be a multiple of 64");
   if (g.ld_out % 8 != 0) return fail(kInvalidArgument, "gemm: ld_out must be a multiple of 8");
   int bn;
-  if (g.mode == 1) {
+  if (g.mode == 1 && g.taps % 4 == 0 && get_option_gemm_impl() != 1) {
+    // tap-paired positional conv (mode 2 in the kernel): N = 256 = 4 taps x 64 output channels per k-block
+    if (g.group_size <= 0 || g.group_size > 64 || g.group_size % 8 != 0 || g.N % g.group_size != 0)
+      return fail(kInvalidArgument, "posconv: channels per group must be a multiple of 8 and <= 64");
+    bn = 256;
+    kp.mode = 2;
+    kp.tiles_per_clip = ceil_div(g.clip_valid, kPosRows);
+    kp.m_tiles = g.n_clips * kp.tiles_per_clip;
+    kp.n_tiles = g.N / g.group_size;
+    kp.n_stride = g.group_size;
+    kp.n_valid = g.group_size;
+    kp.num_kb = g.taps / 4;
+    kp.clip_rows = g.clip_rows;
+    kp.clip_valid = g.clip_valid;
+    kp.pad_left = g.pad_left;
+  } else if (g.mode == 1) {
     bn = 64;
     if (g.group_size <= 0 || g.group_size > 64 || g.group_size % 8 != 0 || g.N % g.group_size != 0)
       return fail(kInvalidArgument, "posconv: channels per group must be a multiple of 8 and <= 64");

@@ -98,9 +98,12 @@ def test_gemm_conv_view(k, stride):
 
 
 @pytest.mark.parametrize("D,groups,T,Ta,B", [(1024, 16, 499, 500, 2), (1024, 16, 49, 50, 3), (768, 16, 130, 132, 2)])
-def test_posconv(D, groups, T, Ta, B):
+@pytest.mark.parametrize("impl,taps", [(0, 128), (1, 128), (0, 16), (0, 30)])
+def test_posconv(D, groups, T, Ta, B, impl, taps):
+    """impl 0: tap-paired kernel mode (four taps per k-block, N = 256) when taps % 4 == 0; impl 1 / other tap counts: one tap
+    per k-block (N = 64).  Odd-length kernels keep every output frame, even ones drop the last (HF SamePad)."""
     from svt_speechbrain_b200._lib import check, current_stream_ptr, lib, ptr
-    taps = 128
+    check(lib().svt_set_option(b"gemm_impl", impl))
     Dg = D // groups
     g = torch.Generator(device="cuda").manual_seed(D + T)
     x = torch.randn(B, Ta, D, device="cuda", generator=g).bfloat16()
@@ -115,11 +118,14 @@ def test_posconv(D, groups, T, Ta, B):
         p[:, :, :Dg, :Dg] = w.view(groups, Dg, Dg, taps).permute(0, 3, 1, 2)
         packed = p.bfloat16().contiguous().view(-1)
     out = resid.clone()
-    check(lib().svt_op_posconv(ptr(x), ptr(packed), ptr(bias), ptr(out), ptr(out), B, Ta, T, D, groups, taps,
-                               current_stream_ptr()))
-    torch.cuda.synchronize()
+    try:
+        check(lib().svt_op_posconv(ptr(x), ptr(packed), ptr(bias), ptr(out), ptr(out), B, Ta, T, D, groups, taps,
+                                   current_stream_ptr()))
+        torch.cuda.synchronize()
+    finally:
+        check(lib().svt_set_option(b"gemm_impl", 0))
     xv = x[:, :T].float().permute(0, 2, 1)
-    conv = torch.nn.functional.conv1d(xv, w, bias, padding=taps // 2, groups=groups)[:, :, :-1]
+    conv = torch.nn.functional.conv1d(xv, w, bias, padding=taps // 2, groups=groups)[:, :, :T]
     ref = resid[:, :T] + torch.nn.functional.gelu(conv).permute(0, 2, 1)
     err = (out[:, :T] - ref).abs().max().item()
     print(f"posconv D={D} T={T}: max abs err {err:.3e}")

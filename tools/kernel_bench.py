@@ -103,6 +103,18 @@ def main():
         gemm("conv1 k3s2 (implicit)", 1024000, 512, 1536, k_inner=512, row_stride=1024, out=out)
         gemm("conv2 k3s2 (implicit)", 512000, 512, 1536, k_inner=512, row_stride=1024, out=out)
         gemm("conv5 k2s2 (implicit)", 64000, 512, 1024, k_inner=512, row_stride=1024, out=out)
+    if "posconv" in which or "conv" in which:
+        D, G, taps = 1024, 16, 128
+        x = torch.randn(B * Ta, D, device=dev).bfloat16()
+        wpk = (torch.randn(G * taps * 64, 64, device=dev) * 0.01).bfloat16()
+        bias = torch.zeros(D, device=dev)
+        h = torch.randn(B * Ta, D, device=dev)
+        s_ = current_stream_ptr()
+        fn = lambda: check(lib().svt_op_posconv(ptr(x), ptr(wpk), ptr(bias), ptr(h), ptr(h), B, Ta, T, D, G, taps, s_))
+        us = timeit(fn)
+        tf = 2.0 * B * T * D * (D // G) * taps / us / 1e6
+        print(f"{'posconv k=128 g=16 (+gelu +resid)':34s} clips={B} T={T} D={D}  {us:9.1f} us  {tf:7.1f} TFLOP/s", flush=True)
+        out["posconv"] = {"us": us, "tflops": tf}
     if "attn" in which:
         attention("attention mma.sync dh64", 1, B, 16, T, Ta, 64, out=out)
         attention("attention tcgen05 dh64", 2, B, 16, T, Ta, 64, out=out)

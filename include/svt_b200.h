@@ -88,6 +88,11 @@ int svt_encoder_set_tensor(svt_encoder* enc, const char* name, const float* host
                            int strict);
 /* AMT head = speechbrain Linear: w (n_out, D) fp32 host, b (n_out) or NULL; n_out <= 32 */
 int svt_encoder_set_head(svt_encoder* enc, const float* w, const float* b, int n_out);
+/* Scope of the two whole-tensor layer norms (huggingface_interface.py:288-289,295-296).  0 (default): one mean / variance
+ * over the whole call, exactly what one reference forward of a (B, L) batch computes.  1: one per clip, i.e. what B
+ * separate reference calls of batch size 1 compute -- the reference's evaluation loop (train_audio_ssl.py:85-90 asserts
+ * batch size 1), so a batch of utterances reproduces that loop in one call. */
+int svt_encoder_set_norm_per_clip(svt_encoder* enc, int per_clip);
 /* Pack into kernel layouts on the device (bf16 cast, conv weights tap-major, QKV concatenation with the
  * d_h^-0.5 scale folded into q, weight-norm recomposition).  May be called again after set_tensor. */
 int svt_encoder_finalize(svt_encoder* enc);

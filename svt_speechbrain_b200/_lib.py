@@ -52,6 +52,7 @@ _SIGS = {
     "svt_encoder_set_tensor": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, C.c_int]),
     "svt_encoder_set_head": (C.c_int, [_P, _P, _P, C.c_int]),
     "svt_encoder_finalize": (C.c_int, [_P]),
+    "svt_encoder_set_norm_per_clip": (C.c_int, [_P, C.c_int]),
     "svt_encoder_num_frames": (C.c_int, [_P, C.c_int]),
     "svt_encoder_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
     "svt_encoder_forward": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P, _P, _P]),

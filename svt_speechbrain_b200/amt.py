@@ -68,9 +68,16 @@ class AMTTranscriber:
         return eng
 
     @torch.no_grad()
-    def logits(self, wav: torch.Tensor) -> torch.Tensor:
-        """wav (B, L) CUDA fp32 -> frame logits (B, T, 20) CUDA fp32 (encoder + output norm + head fused)."""
-        _, lg = self._engine().forward(wav, want_feats=False, want_logits=True)
+    def logits(self, wav: torch.Tensor, per_clip_norm: bool = False) -> torch.Tensor:
+        """wav (B, L) CUDA fp32 -> frame logits (B, T, 20) CUDA fp32 (encoder + output norm + head fused).
+        per_clip_norm: the two whole-tensor layer norms use one mean / variance per clip, i.e. the result of B separate
+        reference calls of batch size 1 (the reference's evaluation loop) computed in one batched call."""
+        eng = self._engine()
+        eng.set_norm_per_clip(per_clip_norm)
+        try:
+            _, lg = eng.forward(wav, want_feats=False, want_logits=True)
+        finally:
+            eng.set_norm_per_clip(False)
         return lg
 
     def frame_info(self, logits: torch.Tensor):
@@ -100,27 +107,60 @@ class AMTTranscriber:
     def transcribe_song(self, wav: torch.Tensor, dur: Optional[float] = None, batch_clips: int = 64,
                         per_clip_norm: bool = True) -> np.ndarray:
         """wav: 1-D waveform of a whole song.  Utterances are cut by the reference rule, run through the
-        encoder, concatenated in order and decoded once.  per_clip_norm=True reproduces the reference
-        evaluation loop (batch size 1: the whole-tensor norms see one utterance at a time); equal-length
-        utterances are still batched on the device, one forward per utterance only when per_clip_norm."""
+        encoder, concatenated in order and decoded once.  Equal-length utterances are batched on the device.
+        per_clip_norm=True reproduces the reference evaluation loop (batch size 1: the whole-tensor norms see one
+        utterance at a time) with the per-clip normalisation scope of the encoder, still in batched calls."""
         wav = wav.to(self.device, torch.float32).reshape(-1)
         spans = split_song(wav.numel(), self.hp, dur)
         pieces: List[torch.Tensor] = []
-        if per_clip_norm:
-            for a, b in spans:
-                pieces.append(self.logits(wav[a:b].unsqueeze(0))[0])
-        else:
-            i = 0
-            while i < len(spans):
-                j = i
-                L = spans[i][1] - spans[i][0]
-                while j < len(spans) and j - i < batch_clips and spans[j][1] - spans[j][0] == L:
-                    j += 1
-                clips = torch.stack([wav[a:b] for a, b in spans[i:j]])
-                lg = self.logits(clips)
-                pieces.extend(lg[k] for k in range(lg.shape[0]))
-                i = j
+        i = 0
+        while i < len(spans):
+            j = i
+            L = spans[i][1] - spans[i][0]
+            while j < len(spans) and j - i < batch_clips and spans[j][1] - spans[j][0] == L:
+                j += 1
+            clips = torch.stack([wav[a:b] for a, b in spans[i:j]])
+            if per_clip_norm and j - i > 1 and L % 4 != 0:  # unaligned clip length: one call per utterance
+                lg = torch.cat([self.logits(c.unsqueeze(0)) for c in clips], dim=0)
+            else:  # a single clip is its own normalisation scope either way
+                lg = self.logits(clips, per_clip_norm=per_clip_norm and j - i > 1)
+            pieces.extend(lg[k] for k in range(lg.shape[0]))
+            i = j
         return self.decode(torch.cat(pieces, dim=0))
+
+    @torch.no_grad()
+    def transcribe_songs(self, wavs: Sequence[torch.Tensor], dur: Optional[float] = None, batch_clips: int = 64,
+                         per_clip_norm: bool = True) -> List[np.ndarray]:
+        """Evaluation driver replacing the reference's one-utterance-at-a-time loop (speechbrain/core.py:1221-1226,
+        train_audio_ssl.py:85-141): utterances of ALL songs are pooled, equal-length ones run in batches of `batch_clips`
+        (per-clip normalisation = reference semantics), frames are put back in (song, utterance) order (:88,100) and every
+        song is decoded once."""
+        hp = self.hp
+        songs = [w.to(self.device, torch.float32).reshape(-1) for w in wavs]
+        jobs = []  # (length, song, utterance index, start, stop)
+        for si, w in enumerate(songs):
+            for ui, (a, b) in enumerate(split_song(w.numel(), hp, dur)):
+                jobs.append((b - a, si, ui, a, b))
+        out = {}
+        jobs.sort(key=lambda t: (t[0], t[1], t[2]))
+        i = 0
+        while i < len(jobs):
+            j = i
+            while j < len(jobs) and j - i < batch_clips and jobs[j][0] == jobs[i][0]:
+                j += 1
+            clips = torch.stack([songs[si][a:b] for _, si, _, a, b in jobs[i:j]])
+            if per_clip_norm and jobs[i][0] % 4 != 0 and j - i > 1:
+                lg = torch.cat([self.logits(c.unsqueeze(0)) for c in clips], dim=0)
+            else:
+                lg = self.logits(clips, per_clip_norm=per_clip_norm and j - i > 1)
+            for k, (_, si, ui, _, _) in enumerate(jobs[i:j]):
+                out[(si, ui)] = lg[k]
+            i = j
+        results = []
+        for si, w in enumerate(songs):
+            n_utt = len(split_song(w.numel(), hp, dur))
+            results.append(self.decode(torch.cat([out[(si, ui)] for ui in range(n_utt)], dim=0)))
+        return results
 
 
 class AVTranscriber:

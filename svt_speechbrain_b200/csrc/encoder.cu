@@ -285,7 +285,7 @@ EncPlan make_plan(const svt_encoder* e, int B, int L) {
   const size_t C = c.conv_dim, D = c.hidden_size, F = c.ffn_size;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
-  p.off_stats = take(64);
+  p.off_stats = take(64 + sizeof(double) * 4 * static_cast<size_t>(B));  // [B][2] input + [B][2] output statistics
   p.off_chan = take(sizeof(double) * 2 * C * B);
   const size_t slack = 2 * C * 8 * 2;  // overlapping conv rows read up to (k - stride) * C elements past the end
   p.off_bufA = take(static_cast<size_t>(B) * p.T0a * C * 2 + slack);
@@ -321,7 +321,7 @@ int linear(const __nv_bfloat16* a, int M, const LinearW& w, const float* resid, 
 // if stats_out != nullptr it receives sum / sum-of-squares of those rows over t < T (whole-tensor output norm).
 namespace svt {
 int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, const TransformerBuffers& tb, double* stats_out,
-                                const float** final_x_out, cudaStream_t s) {
+                                int stats_stride, const float** final_x_out, cudaStream_t s) {
   const svt_encoder_config& c = e->cfg;
   const int D = c.hidden_size, H = c.num_heads, dh = D / H;
   const int M = B * Ta;
@@ -353,6 +353,7 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
     LayerNormArgs ln;
     ln.x_f32 = x; ln.gamma = w.g; ln.beta = w.b; ln.y_bf16 = yb; ln.y_f32 = yf;
     ln.rows = M; ln.D = D; ln.eps = eps; ln.stats = stats; ln.clip_rows = Ta; ln.clip_valid = T;
+    ln.stats_stride = stats_stride;
     return layer_norm(ln, s);
   };
   auto attend = [&]() {
@@ -362,7 +363,7 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
     a.Tq = T; a.Tk = T; a.q_clip_rows = Ta; a.k_clip_rows = Ta; a.clips = B; a.heads = H; a.head_dim = dh;
     return attention_bf16(a, s);
   };
-  if (want_stats) SVT_CUDA(cudaMemsetAsync(stats_out, 0, 2 * sizeof(double), s));
+  if (want_stats) SVT_CUDA(cudaMemsetAsync(stats_out, 0, 2 * sizeof(double) * (stats_stride > 0 ? B : 1), s));
   const float* final_x = nullptr;
 
   if (c.stable_layer_norm) {
@@ -413,7 +414,8 @@ static int forward_impl(svt_encoder* e, const float* wav, int B, int L, void* ws
   if (logits != nullptr && e->head_w == nullptr) return fail(kInvalidArgument, "logits requested but no head set");
   uint8_t* base = static_cast<uint8_t*>(ws);
   double* stats_in = reinterpret_cast<double*>(base + p.off_stats);
-  double* stats_out = stats_in + 2;
+  double* stats_out = stats_in + 2 * static_cast<size_t>(B);
+  const int stats_stride = e->norm_per_clip ? 2 : 0;
   double* chan = reinterpret_cast<double*>(base + p.off_chan);
   __nv_bfloat16* bufA = reinterpret_cast<__nv_bfloat16*>(base + p.off_bufA);
   __nv_bfloat16* bufB = reinterpret_cast<__nv_bfloat16*>(base + p.off_bufB);
@@ -427,12 +429,16 @@ static int forward_impl(svt_encoder* e, const float* wav, int B, int L, void* ws
   const float eps = c.layer_norm_eps;
 
   // ---- A1 + conv layer 0 (fused input normalisation)
-  if (c.normalize_wav) SVT_TRY(tensor_stats(wav, static_cast<size_t>(B) * L, stats_in, s));
+  if (c.normalize_wav) {
+    if (stats_stride > 0) SVT_TRY(tensor_stats_per_clip(wav, B, static_cast<size_t>(L), stats_in, s));
+    else SVT_TRY(tensor_stats(wav, static_cast<size_t>(B) * L, stats_in, s));
+  }
   Conv0Args c0;
   c0.wav = wav; c0.B = B; c0.L = L; c0.T = e->conv_out_len(L, 0); c0.t_alloc = p.T0a;
   c0.C = C; c0.k = c.conv_kernel[0]; c0.stride = c.conv_stride[0];
   c0.w = e->conv0_w; c0.bias = e->conv0_b; c0.gamma = e->conv0_norm.g; c0.beta = e->conv0_norm.b;
   c0.in_stats = c.normalize_wav ? stats_in : nullptr;
+  c0.stats_stride = stats_stride;
   c0.out = bufA; c0.layer_mode = c.feat_norm_layer; c0.chan_stats = chan;
   SVT_TRY(conv0_forward(c0, s));
   if (!c.feat_norm_layer)
@@ -480,12 +486,12 @@ static int forward_impl(svt_encoder* e, const float* wav, int B, int L, void* ws
   {
     TransformerBuffers tb;
     tb.h = h; tb.hb = hb; tb.qkv = qkv; tb.ctx = ctx; tb.mid = mid; tb.pre = pre;
-    SVT_TRY(encoder_transformer_forward(e, B, T, Ta, tb, want_stats ? stats_out : nullptr, &final_x, s));
+    SVT_TRY(encoder_transformer_forward(e, B, T, Ta, tb, want_stats ? stats_out : nullptr, stats_stride, &final_x, s));
   }
   // ---- A7 whole-tensor output norm + head
   HeadArgs ha;
   ha.x = final_x; ha.clips = B; ha.clip_rows = Ta; ha.T = T; ha.D = D;
-  ha.stats = want_stats ? stats_out : nullptr; ha.eps = 1e-5f;
+  ha.stats = want_stats ? stats_out : nullptr; ha.eps = 1e-5f; ha.stats_stride = stats_stride;
   ha.w = logits != nullptr ? e->head_w : nullptr; ha.b = e->head_b; ha.n_out = e->head_n;
   ha.feats = feats; ha.logits = logits;
   if (feats != nullptr || logits != nullptr) SVT_TRY(head_forward(ha, s));
@@ -544,6 +550,12 @@ int svt_encoder_set_head(svt_encoder* enc, const float* w, const float* b, int n
   if (b != nullptr) SVT_CUDA(cudaMemcpy(enc->head_b, b, sizeof(float) * n_out, cudaMemcpyHostToDevice));
   else SVT_CUDA(cudaMemset(enc->head_b, 0, sizeof(float) * n_out));
   enc->head_n = n_out;
+  return kOk;
+}
+
+int svt_encoder_set_norm_per_clip(svt_encoder* enc, int per_clip) {
+  if (enc == nullptr) return fail(kInvalidArgument, "null argument");
+  enc->norm_per_clip = per_clip != 0;
   return kOk;
 }
 

@@ -87,6 +87,7 @@ struct svt_encoder {
   svt::WeightRegistry reg;
   svt::DevicePool pool;
   bool finalized = false;
+  bool norm_per_clip = false;     // whole-tensor norms use one (mean, var) per clip instead of one per call
   bool transformer_only = false;  // AV-HuBERT video stream: only the positional conv + layers are packed
 
   // packed weights
@@ -117,7 +118,7 @@ struct svt_encoder {
 namespace svt {
 int encoder_finalize(svt_encoder* e);
 int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, const TransformerBuffers& tb, double* stats_out,
-                                const float** final_x_out, cudaStream_t s);
+                                int stats_stride, const float** final_x_out, cudaStream_t s);
 }  // namespace svt
 
 struct svt_fusion {

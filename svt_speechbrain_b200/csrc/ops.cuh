@@ -36,13 +36,16 @@ struct LayerNormArgs {
   float eps = 1e-5f;
   int gelu = 0;
   // optional: accumulate sum / sum-of-squares of the fp32 OUTPUT over rows with (row % clip_rows) < clip_valid
-  double* stats = nullptr;  // [2]
+  double* stats = nullptr;  // [2], or [clips][2] when stats_stride == 2 (per-clip statistics)
   int clip_rows = 0, clip_valid = 0;
+  int stats_stride = 0;
 };
 int layer_norm(const LayerNormArgs& a, cudaStream_t stream);
 
 // sum / sum of squares of an fp32 tensor (whole-tensor layer norm, huggingface_interface.py:289)
 int tensor_stats(const float* x, size_t n, double* stats /*[2], zeroed here*/, cudaStream_t stream);
+// the same per clip: x (clips, n_per_clip) -> stats [clips][2]
+int tensor_stats_per_clip(const float* x, int clips, size_t n_per_clip, double* stats, cudaStream_t stream);
 
 // conv layer 0 (C_in = 1): wav (B, L) fp32 -> (B, t_alloc, C) bf16 channel-last.
 //   layer mode : (x - mean) * rstd -> conv(k, s) + bias -> LN over C -> GELU          (large)
@@ -56,6 +59,7 @@ struct Conv0Args {
   const float* gamma = nullptr; // LN affine (layer mode)
   const float* beta = nullptr;
   const double* in_stats = nullptr;  // [2] sum, sumsq over the B*L input (null: no input normalisation)
+  int stats_stride = 0;              // 2: in_stats is [B][2], every clip normalised by its own statistics
   __nv_bfloat16* out = nullptr;
   int layer_mode = 1;
   double* chan_stats = nullptr;  // group mode: [B][C][2] sums (zeroed by the launcher)
@@ -72,7 +76,8 @@ int groupnorm_gelu_apply(__nv_bfloat16* x, const double* chan_stats, const float
 struct HeadArgs {
   const float* x = nullptr;  // [clips*clip_rows, D] fp32
   int clips = 0, clip_rows = 0, T = 0, D = 0;
-  const double* stats = nullptr;  // [2] or null (no output norm)
+  const double* stats = nullptr;  // [2] or null (no output norm); [clips][2] when stats_stride == 2
+  int stats_stride = 0;
   float eps = 1e-5f;
   const float* w = nullptr;  // [n_out, D] fp32 (null: no head)
   const float* b = nullptr;

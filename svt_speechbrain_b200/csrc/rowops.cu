@@ -38,7 +38,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 layer_norm_kernel(const float* __restrict__ xf, const __nv_bfloat16* __restrict__ xb, const float* __restrict__ gamma,
                   const float* __restrict__ beta, __nv_bfloat16* __restrict__ yb, float* __restrict__ yf, int rows,
-                  float eps, int gelu, double* __restrict__ stats, int clip_rows, int clip_valid) {
+                  float eps, int gelu, double* __restrict__ stats, int clip_rows, int clip_valid, int stats_stride) {
   constexpr int D = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
@@ -79,7 +79,15 @@ layer_norm_kernel(const float* __restrict__ xf, const __nv_bfloat16* __restrict_
     }
     if (stats != nullptr && (row % clip_rows) >= clip_valid) { s_out = 0.f; ss_out = 0.f; }
   }
-  if (stats != nullptr) {
+  if (stats != nullptr && stats_stride > 0) {
+    // per-clip statistics: a block's 8 rows may straddle two clips, so every warp (= row) adds to its own clip's pair
+    const float a = warp_sum(s_out), b = warp_sum(ss_out);
+    if (lane == 0 && row < rows) {
+      double* st = stats + static_cast<size_t>(row / clip_rows) * stats_stride;
+      atomicAdd(st, static_cast<double>(a));
+      atomicAdd(st + 1, static_cast<double>(b));
+    }
+  } else if (stats != nullptr) {
     __shared__ double sh[8];
     const double a = block_sum_double(static_cast<double>(s_out), sh);
     const double b = block_sum_double(static_cast<double>(ss_out), sh);
@@ -88,7 +96,11 @@ layer_norm_kernel(const float* __restrict__ xf, const __nv_bfloat16* __restrict_
 }
 
 // ------------------------------------------------------------------------------------ tensor stats
-__global__ void __launch_bounds__(256) tensor_stats_kernel(const float* __restrict__ x, size_t n, double* stats) {
+// blockIdx.y = segment (clip): x + y * seg_stride, stats + y * stats_stride (both 0 for the whole-tensor form)
+__global__ void __launch_bounds__(256) tensor_stats_kernel(const float* __restrict__ x, size_t n, double* stats,
+                                                           size_t seg_stride, int stats_stride) {
+  x += static_cast<size_t>(blockIdx.y) * seg_stride;
+  stats += static_cast<size_t>(blockIdx.y) * stats_stride;
   float s = 0.f, ss = 0.f;
   const size_t n4 = n / 4;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -126,7 +138,7 @@ __global__ void __launch_bounds__(256)
 conv0_kernel(const float* __restrict__ wav, int L, int T, int t_alloc, const float* __restrict__ w,
              const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
              const double* __restrict__ in_stats, double n_in, __nv_bfloat16* __restrict__ out,
-             double* __restrict__ chan_stats) {
+             double* __restrict__ chan_stats, int stats_stride) {
   __shared__ __align__(16) float sw[kK0 * kC0];
   __shared__ __align__(16) float sbias[kC0];
   __shared__ __align__(16) float sgamma[kC0];
@@ -139,7 +151,7 @@ conv0_kernel(const float* __restrict__ wav, int L, int T, int t_alloc, const flo
   }
   __syncthreads();
   float mean = 0.f, rstd = 1.f;
-  if (in_stats != nullptr) mean_rstd_from_stats(in_stats, n_in, 1e-5f, mean, rstd);
+  if (in_stats != nullptr) mean_rstd_from_stats(in_stats + static_cast<size_t>(blockIdx.y) * stats_stride, n_in, 1e-5f, mean, rstd);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int clip = blockIdx.y;
@@ -263,19 +275,21 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 head_kernel(const float* __restrict__ x, int clips, int clip_rows, int T, const double* __restrict__ stats, float eps,
             const float* __restrict__ w, const float* __restrict__ b, int n_out, float* __restrict__ feats,
-            float* __restrict__ logits, int w_in_smem) {
+            float* __restrict__ logits, int w_in_smem, int stats_stride) {
   constexpr int D = NV * 128;
   extern __shared__ __align__(16) float sw[];
   if (w != nullptr && w_in_smem)
     for (int i = threadIdx.x; i < n_out * D; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
   float mean = 0.f, rstd = 1.f;
-  if (stats != nullptr) mean_rstd_from_stats(stats, static_cast<double>(clips) * T * D, eps, mean, rstd);
+  if (stats != nullptr && stats_stride == 0) mean_rstd_from_stats(stats, static_cast<double>(clips) * T * D, eps, mean, rstd);
   const float* wp = w_in_smem ? sw : w;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = clips * T;
   for (int fr = blockIdx.x * 8 + warp; fr < total; fr += gridDim.x * 8) {
     const int clip = fr / T, t = fr % T;
+    if (stats != nullptr && stats_stride > 0)
+      mean_rstd_from_stats(stats + static_cast<size_t>(clip) * stats_stride, static_cast<double>(T) * D, eps, mean, rstd);
     const float* xr = x + (static_cast<size_t>(clip) * clip_rows + t) * D;
     float4 v[NV];
 #pragma unroll
@@ -396,7 +410,8 @@ int layer_norm(const LayerNormArgs& a, cudaStream_t stream) {
   const int clip_valid = a.clip_rows > 0 ? a.clip_valid : 1;
   return dispatch_nv(a.D, [&](auto nv) {
     layer_norm_kernel<decltype(nv)::value><<<ceil_div(a.rows, 8), 256, 0, stream>>>(
-        a.x_f32, a.x_bf16, a.gamma, a.beta, a.y_bf16, a.y_f32, a.rows, a.eps, a.gelu, a.stats, clip_rows, clip_valid);
+        a.x_f32, a.x_bf16, a.gamma, a.beta, a.y_bf16, a.y_f32, a.rows, a.eps, a.gelu, a.stats, clip_rows, clip_valid,
+        a.stats_stride);
     SVT_POST_LAUNCH();
     return static_cast<int>(kOk);
   });
@@ -406,7 +421,18 @@ int tensor_stats(const float* x, size_t n, double* stats, cudaStream_t stream) {
   SVT_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(double), stream));
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return fail(kInvalidArgument, "tensor_stats: input must be 16-byte aligned");
   const int grid = num_sms() * 4;
-  tensor_stats_kernel<<<grid, 256, 0, stream>>>(x, n, stats);
+  tensor_stats_kernel<<<grid, 256, 0, stream>>>(x, n, stats, 0, 0);
+  SVT_POST_LAUNCH();
+  return kOk;
+}
+
+int tensor_stats_per_clip(const float* x, int clips, size_t n_per_clip, double* stats, cudaStream_t stream) {
+  SVT_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(double) * clips, stream));
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || n_per_clip % 4 != 0)
+    return fail(kInvalidArgument, "per-clip statistics need 16-byte aligned clips (n_samples % 4 == 0)");
+  int gx = (num_sms() * 4 + clips - 1) / clips;
+  if (gx < 1) gx = 1;
+  tensor_stats_kernel<<<dim3(gx, clips), 256, 0, stream>>>(x, n_per_clip, stats, n_per_clip, 2);
   SVT_POST_LAUNCH();
   return kOk;
 }
@@ -417,14 +443,14 @@ int conv0_forward(const Conv0Args& a, cudaStream_t stream) {
   if (a.t_alloc % kR0 != 0) return fail(kInvalidArgument, "conv0: t_alloc % 4 != 0");
   const int groups = a.t_alloc / kR0;
   dim3 grid(ceil_div(groups, 8 * kConv0GroupsPerWarp), a.B);
-  const double n_in = static_cast<double>(a.B) * a.L;
+  const double n_in = a.stats_stride > 0 ? static_cast<double>(a.L) : static_cast<double>(a.B) * a.L;
   if (a.layer_mode) {
     conv0_kernel<true><<<grid, 256, 0, stream>>>(a.wav, a.L, a.T, a.t_alloc, a.w, a.bias, a.gamma, a.beta, a.in_stats,
-                                                 n_in, a.out, nullptr);
+                                                 n_in, a.out, nullptr, a.stats_stride);
   } else {
     SVT_CUDA(cudaMemsetAsync(a.chan_stats, 0, sizeof(double) * 2 * a.C * a.B, stream));
     conv0_kernel<false><<<grid, 256, 0, stream>>>(a.wav, a.L, a.T, a.t_alloc, a.w, a.bias, nullptr, nullptr, a.in_stats,
-                                                  n_in, a.out, a.chan_stats);
+                                                  n_in, a.out, a.chan_stats, a.stats_stride);
   }
   SVT_POST_LAUNCH();
   return kOk;
@@ -456,7 +482,7 @@ int head_forward(const HeadArgs& a, cudaStream_t stream) {
     int grid = ceil_div(a.clips * a.T, 8);
     if (grid > num_sms()) grid = num_sms();
     head_kernel<NV><<<grid, 256, smem, stream>>>(a.x, a.clips, a.clip_rows, a.T, a.stats, a.eps, a.w, a.b, a.n_out,
-                                                 a.feats, a.logits, w_in_smem);
+                                                 a.feats, a.logits, w_in_smem, a.stats_stride);
     SVT_POST_LAUNCH();
     return static_cast<int>(kOk);
   });

@@ -464,7 +464,7 @@ int forward_video(svt_video* v, const float* video, int B, int T, void* ws, size
   // ---- transformer body (fairseq TransformerEncoder == csrc/encoder.cu graph) + whole-tensor output LN
   const bool want_stats = v->cfg.output_norm != 0;
   const float* final_x = nullptr;
-  SVT_TRY(encoder_transformer_forward(v->enc, B, T, Ta, tb, want_stats ? stats_out : nullptr, &final_x, s));
+  SVT_TRY(encoder_transformer_forward(v->enc, B, T, Ta, tb, want_stats ? stats_out : nullptr, 0, &final_x, s));
   HeadArgs ha;
   ha.x = final_x; ha.clips = B; ha.clip_rows = Ta; ha.T = T; ha.D = D;
   ha.stats = want_stats ? stats_out : nullptr; ha.eps = 1e-5f;

@@ -80,6 +80,10 @@ class EncoderEngine:
             check(lib().svt_encoder_set_head(self._h, ptr(w), ptr(b), w.shape[0]))
         self.n_out = w.shape[0]
 
+    def set_norm_per_clip(self, per_clip: bool):
+        """Whole-tensor norms per clip (= the reference's batch-size-1 evaluation loop) instead of per call."""
+        check(lib().svt_encoder_set_norm_per_clip(self._h, int(bool(per_clip))))
+
     def num_frames(self, n_samples: int) -> int:
         return lib().svt_encoder_num_frames(self._h, n_samples)
 

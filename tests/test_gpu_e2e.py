@@ -189,3 +189,37 @@ def test_cpu_tensor_is_rejected_loudly():
     lobe, lin, _, _ = _build(cfg)
     with pytest.raises(RuntimeError):
         lobe(torch.randn(1, 16000))
+
+
+def test_per_clip_norm_scope_equals_batch_size_one_calls():
+    """svt_encoder_set_norm_per_clip: one batched call with per-clip statistics == B separate calls of batch size 1 (the
+    reference's evaluation loop), and both match the oracle run clip by clip."""
+    import svt_speechbrain_b200 as svt
+    from oracle import wav2vec2_oracle as wo
+    cfg = wo.W2V2Config.large()
+    lobe, lin, sd, head = _build(cfg)
+    tr = svt.AMTTranscriber(lobe, lin)
+    wav = torch.randn(3, 16000, generator=torch.Generator().manual_seed(5)) * torch.tensor([[0.2], [1.0], [3.0]])
+    batched = tr.logits(wav.cuda(), per_clip_norm=True).cpu()
+    single = torch.cat([tr.logits(wav[i:i + 1].cuda()) for i in range(3)]).cpu()
+    whole = tr.logits(wav.cuda()).cpu()
+    assert float((batched - single).abs().max()) < 2e-3      # same arithmetic up to the order of the statistics' atomics
+    assert float((batched - whole).abs().max()) > 1e-2       # the scopes really differ on clips of different loudness
+    with torch.no_grad():
+        ref = torch.cat([wo.amt_logits(cfg, sd, head, wav[i:i + 1]) for i in range(3)])
+    _check_logits(batched, ref.numpy(), "per-clip scope vs oracle clip by clip")
+
+
+def test_transcribe_songs_pools_utterances_across_songs():
+    import svt_speechbrain_b200 as svt
+    from oracle import wav2vec2_oracle as wo
+    cfg = wo.W2V2Config.base()
+    lobe, lin, sd, head = _build(cfg)
+    tr = svt.AMTTranscriber(lobe, lin, svt.AMTHparams(dur_threshold=1.0))
+    g = torch.Generator().manual_seed(17)
+    songs = [torch.randn(n, generator=g) for n in (48000, 16000, 40000)]
+    pooled = tr.transcribe_songs(songs)
+    one_by_one = [tr.transcribe_song(w) for w in songs]
+    assert len(pooled) == 3
+    for a, b in zip(pooled, one_by_one):
+        assert a.shape == b.shape and np.allclose(a, b)

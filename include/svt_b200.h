@@ -48,7 +48,8 @@ long long svt_debug_launch_count(void);
 
 /* process-wide tuning / test switches.  "attention_impl": 0 auto (default), 1 force the mma.sync kernel,
  * 2 force the tcgen05/TMEM kernel (head_dim 64 only).  "gemm_impl": 0 auto (CTA-pair cta_group::2 kernel when
- * N % 256 == 0), 1 force the one-CTA kernel. */
+ * N % 256 == 0), 1 force the one-CTA kernel.  "ln_fold": 1 (default) folds the two per-layer LayerNorms of pre-LN
+ * (stable_layer_norm) transformer layers into the neighbouring GEMMs, 0 runs them as separate kernels. */
 int svt_set_option(const char* name, int value);
 
 /* development aid: device buffer of 4 x 256 int64 that CTA 0 of the tcgen05 attention kernel fills with clock64()
@@ -184,6 +185,16 @@ int svt_frame2note(const float* p_on, const float* p_off, const int32_t* oct, co
 int svt_op_gemm(const void* a_bf16, long long a_row_stride, int k_inner, const void* w_bf16, const float* bias,
                 const float* resid, float* out_f32, void* out_bf16, int M, int N, int K, int ld_out, int act,
                 void* stream);
+/* The two halves of a LayerNorm folded around GEMMs (pre-LN transformer layers, option "ln_fold").  Producer
+ * (row_stats_out != NULL, out_f32 != NULL, N % 256 == 0): as svt_op_gemm, and row_stats_out[row][j] = (sum, sum of
+ * squares) of columns 128 j .. 128 j + 127 of the fp32 output row.  Consumer (ln_stats != NULL): a holds un-normalised rows x, w = W o gamma,
+ * colsum[n] = sum_k w[n][k], bias = beta.W + b; out_bf16 = act(rstd * (x.w - mean * colsum) + bias) with mean / rstd
+ * from ln_stats[row][0 .. K / 128) (K in {256, 512, 768, 1024}).  svt_op_row_stats_cast: y = bf16(x) and
+ * stats[row][D / 128][2] written. */
+int svt_op_gemm_ln(const void* a_bf16, const void* w_bf16, const float* bias, const float* colsum, const float* ln_stats,
+                   float ln_eps, float* row_stats_out, const float* resid, float* out_f32, void* out_bf16, int M, int N,
+                   int K, int act, void* stream);
+int svt_op_row_stats_cast(const float* x, int rows, int D, void* y_bf16, float* stats, void* stream);
 /* grouped "same"-padded conv1d over time as used for the positional embedding: x (clips, clip_rows, D) bf16,
  * w packed [G][taps][64][64] bf16, out_f32[row, :] = resid + gelu(conv + bias) for valid rows. */
 int svt_op_posconv(const void* x_bf16, const void* w_packed, const float* bias, const float* resid, float* out_f32,

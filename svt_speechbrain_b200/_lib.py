@@ -74,6 +74,8 @@ _SIGS = {
                                  C.POINTER(C.c_int)]),
     "svt_op_gemm": (C.c_int, [_P, C.c_longlong, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                               C.c_int, _P]),
+    "svt_op_gemm_ln": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "svt_op_row_stats_cast": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "svt_op_posconv": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "svt_op_pack_posconv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "svt_op_attention": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

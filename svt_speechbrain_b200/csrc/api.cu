@@ -18,6 +18,8 @@ void note_kernel_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); 
 long long launch_count() { return g_launches.load(); }
 static std::atomic<int> g_attention_impl{0};
 static std::atomic<int> g_gemm_impl{0};
+static std::atomic<int> g_ln_fold{1};
+int get_option_ln_fold() { return g_ln_fold.load(std::memory_order_relaxed); }
 int get_option_gemm_impl() { return g_gemm_impl.load(std::memory_order_relaxed); }
 int get_option_attention_impl() { return g_attention_impl.load(std::memory_order_relaxed); }
 int num_sms() {
@@ -51,6 +53,11 @@ int svt_set_option(const char* name, int value) {
   if (n == "gemm_impl") {
     if (value < 0 || value > 1) return fail(kInvalidArgument, "gemm_impl must be 0 (auto) or 1 (one-CTA kernel)");
     g_gemm_impl.store(value);
+    return kOk;
+  }
+  if (n == "ln_fold") {
+    if (value < 0 || value > 1) return fail(kInvalidArgument, "ln_fold must be 0 (separate LayerNorm kernels) or 1 (folded)");
+    g_ln_fold.store(value);
     return kOk;
   }
   return fail(kInvalidArgument, "unknown option " + n);
@@ -88,6 +95,27 @@ int svt_op_gemm(const void* a_bf16, long long a_row_stride, int k_inner, const v
   g.bias = bias; g.resid = resid; g.out_f32 = out_f32; g.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16);
   g.ld_out = ld_out; g.act = act;
   return gemm_bf16_tc(g, static_cast<cudaStream_t>(stream));
+}
+
+int svt_op_gemm_ln(const void* a_bf16, const void* w_bf16, const float* bias, const float* colsum, const float* ln_stats,
+                   float ln_eps, float* row_stats_out, const float* resid, float* out_f32, void* out_bf16, int M, int N,
+                   int K, int act, void* stream) {
+  if (a_bf16 == nullptr || w_bf16 == nullptr) return fail(kInvalidArgument, "null argument");
+  GemmArgs g;
+  g.a = static_cast<const __nv_bfloat16*>(a_bf16);
+  g.a_dims[0] = K; g.a_dims[1] = 1; g.a_dims[2] = M;
+  g.a_strides[0] = K; g.a_strides[1] = static_cast<uint64_t>(K);
+  g.w = static_cast<const __nv_bfloat16*>(w_bf16); g.w_rows = N; g.w_cols = K;
+  g.M = M; g.N = N; g.K = K; g.k_inner = K;
+  g.bias = bias; g.resid = resid; g.out_f32 = out_f32; g.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16);
+  g.ld_out = N; g.act = act;
+  g.row_stats_out = row_stats_out; g.ln_stats = ln_stats; g.ln_colsum = colsum; g.ln_eps = ln_eps;
+  return gemm_bf16_tc(g, static_cast<cudaStream_t>(stream));
+}
+
+int svt_op_row_stats_cast(const float* x, int rows, int D, void* y_bf16, float* stats, void* stream) {
+  if (x == nullptr || y_bf16 == nullptr || stats == nullptr) return fail(kInvalidArgument, "null argument");
+  return row_stats_cast(x, rows, D, static_cast<__nv_bfloat16*>(y_bf16), stats, static_cast<cudaStream_t>(stream));
 }
 
 int svt_op_pack_posconv(const float* w_f32_dev, int D, int groups, int taps, void* out_bf16, void* stream) {

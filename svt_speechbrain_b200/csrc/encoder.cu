@@ -85,13 +85,21 @@ int pack_norm(DevicePool& pool, const WeightRegistry& reg, const std::string& pr
   return pack_vec(pool, reg, prefix + "bias", n, 1.f, &out->b);
 }
 // dst rows [row0, row0+N) of a [*, K] bf16 matrix <- scale * src (N, K)
-int pack_rows(const RawTensor* t, int N, int K, float scale, __nv_bfloat16* dst, int row0) {
+int pack_rows(const RawTensor* t, int N, int K, float scale, __nv_bfloat16* dst, int row0, const float* col_scale = nullptr) {
   PackArgs a;
   a.src = t->dev;
   a.dims[2] = N; a.dims[3] = K;
   a.strides[2] = K; a.strides[3] = 1;
   a.scale = scale;
+  a.vec = col_scale; a.vec_dim = 3;
   return pack_bf16(a, dst + static_cast<size_t>(row0) * K, 0);
+}
+// LayerNorm(gamma, beta) folded into the Linear that consumes it: rows [row0, row0 + N) of dst.w <- scale * W o gamma,
+// dst.colsum <- row sums of the packed bf16 weight, dst.b (already scale * b) += scale * W.beta
+int fold_norm_rows(const RawTensor* w, int N, int K, float scale, const NormW& norm, LinearW* dst, int row0) {
+  SVT_TRY(pack_rows(w, N, K, scale, dst->w, row0, norm.g));
+  return ln_fold_vectors(w->dev, dst->w + static_cast<size_t>(row0) * K, norm.b, scale, N, K, dst->colsum + row0,
+                         dst->b + row0, 0);
 }
 int pack_linear(DevicePool& pool, const WeightRegistry& reg, const std::string& prefix, int N, int K, LinearW* out) {
   const RawTensor* w;
@@ -258,6 +266,27 @@ int svt::encoder_finalize(svt_encoder* e) {
     SVT_TRY(pack_linear(pool, reg, p + "attention.out_proj.", D, D, &L.out));
     SVT_TRY(pack_linear(pool, reg, p + "feed_forward.intermediate_dense.", F, D, &L.ff1));
     SVT_TRY(pack_linear(pool, reg, p + "feed_forward.output_dense.", D, F, &L.ff2));
+    if (transformer_rowstats_bytes(e, 1) > 0) {
+      // second copies of the two Linears that read a LayerNorm, with the norm folded in
+      L.qkv_ln.N = 3 * D; L.qkv_ln.K = D;
+      SVT_TRY(pool.alloc_t<__nv_bfloat16>(static_cast<size_t>(3) * D * D, &L.qkv_ln.w));
+      SVT_TRY(pool.alloc_t<float>(static_cast<size_t>(3) * D, &L.qkv_ln.b));
+      SVT_TRY(pool.alloc_t<float>(static_cast<size_t>(3) * D, &L.qkv_ln.colsum));
+      SVT_CUDA(cudaMemcpy(L.qkv_ln.b, L.qkv.b, sizeof(float) * 3 * D, cudaMemcpyDeviceToDevice));
+      for (int j = 0; j < 3; ++j) {
+        const RawTensor* w;
+        SVT_TRY(reg.require(p + "attention." + names[j] + "weight", {D, D}, &w));
+        SVT_TRY(fold_norm_rows(w, D, D, (j == 0) ? qscale : 1.f, L.ln1, &L.qkv_ln, j * D));
+      }
+      L.ff1_ln.N = F; L.ff1_ln.K = D;
+      SVT_TRY(pool.alloc_t<__nv_bfloat16>(static_cast<size_t>(F) * D, &L.ff1_ln.w));
+      SVT_TRY(pool.alloc_t<float>(static_cast<size_t>(F), &L.ff1_ln.b));
+      SVT_TRY(pool.alloc_t<float>(static_cast<size_t>(F), &L.ff1_ln.colsum));
+      SVT_CUDA(cudaMemcpy(L.ff1_ln.b, L.ff1.b, sizeof(float) * F, cudaMemcpyDeviceToDevice));
+      const RawTensor* w;
+      SVT_TRY(reg.require(p + "feed_forward.intermediate_dense.weight", {F, D}, &w));
+      SVT_TRY(fold_norm_rows(w, F, D, 1.f, L.ln2, &L.ff1_ln, 0));
+    }
     e->layers.push_back(L);
   }
   SVT_CUDA(cudaDeviceSynchronize());
@@ -270,7 +299,7 @@ int svt::encoder_finalize(svt_encoder* e) {
 namespace {
 struct EncPlan {
   int B, L, T0a, Tn, Tna, M;  // Tn: valid output frames, Tna: allocated frames per clip, M = B * Tna
-  size_t off_stats, off_chan, off_bufA, off_bufB, off_h, off_hb, off_qkv, off_ctx, off_mid, off_pre, total;
+  size_t off_stats, off_chan, off_bufA, off_bufB, off_h, off_hb, off_qkv, off_ctx, off_mid, off_pre, off_rowstats, total;
 };
 EncPlan make_plan(const svt_encoder* e, int B, int L) {
   const svt_encoder_config& c = e->cfg;
@@ -297,13 +326,16 @@ EncPlan make_plan(const svt_encoder* e, int B, int L) {
   p.off_ctx = take(static_cast<size_t>(p.M) * D * 2);
   p.off_mid = take(static_cast<size_t>(p.M) * F * 2);
   p.off_pre = take(static_cast<size_t>(p.M) * D * 4);
+  p.off_rowstats = take(transformer_rowstats_bytes(e, static_cast<size_t>(p.M)));
   p.total = off;
   return p;
 }
 
 int linear(const __nv_bfloat16* a, int M, const LinearW& w, const float* resid, float* out_f32, __nv_bfloat16* out_bf16,
-           int act, cudaStream_t s) {
+           int act, cudaStream_t s, float* row_stats_out = nullptr, const float* ln_stats = nullptr, float ln_eps = 0.f) {
   GemmArgs g;
+  g.row_stats_out = row_stats_out;
+  if (ln_stats != nullptr) { g.ln_stats = ln_stats; g.ln_colsum = w.colsum; g.ln_eps = ln_eps; }
   g.a = a;
   g.a_dims[0] = w.K; g.a_dims[1] = 1; g.a_dims[2] = M;
   g.a_strides[0] = w.K; g.a_strides[1] = w.K;
@@ -320,6 +352,12 @@ int linear(const __nv_bfloat16* a, int M, const LinearW& w, const float* resid, 
 // hb (its bf16 copy), rows = clip * Ta + t.  Out: *final_x points at the fp32 rows to normalise / hand to the head;
 // if stats_out != nullptr it receives sum / sum-of-squares of those rows over t < T (whole-tensor output norm).
 namespace svt {
+size_t transformer_rowstats_bytes(const svt_encoder* e, size_t M) {
+  // two [M][D / 128][2] fp32 buffers; 0 when the LayerNorm fold does not apply (post-LN model or unsupported width)
+  const int D = e->cfg.hidden_size;
+  const bool ok = e->cfg.stable_layer_norm && D % 256 == 0 && D <= 1024;
+  return ok ? sizeof(float) * 2 * M * static_cast<size_t>(D / 128) * 2 : 0;
+}
 int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, const TransformerBuffers& tb, double* stats_out,
                                 int stats_stride, const float** final_x_out, cudaStream_t s) {
   const svt_encoder_config& c = e->cfg;
@@ -366,7 +404,24 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
   if (want_stats) SVT_CUDA(cudaMemsetAsync(stats_out, 0, 2 * sizeof(double) * (stats_stride > 0 ? B : 1), s));
   const float* final_x = nullptr;
 
-  if (c.stable_layer_norm) {
+  if (c.stable_layer_norm && get_option_ln_fold() != 0 && c.num_layers > 0 && transformer_rowstats_bytes(e, M) > 0) {
+    // pre-LN layers (HF:612-655) with both per-layer LayerNorms folded around the GEMMs: the GEMM that writes the
+    // residual stream also writes its bf16 copy and per-row (sum, sum of squares); the GEMM that reads LN(h) runs on
+    // the un-normalised copy with gamma folded into W and finishes the normalisation in its epilogue.
+    float* st = tb.rowstats;                                    // statistics of the rows entering a layer
+    float* st_mid = st + 2 * static_cast<size_t>(M) * (D / 128);  // ... and of the rows after the attention block
+    SVT_TRY(row_stats_cast(h, M, D, hb, st, s));
+    for (int l = 0; l < c.num_layers; ++l) {
+      const svt_encoder::Layer& Lw = e->layers[l];
+      SVT_TRY(linear(hb, M, Lw.qkv_ln, nullptr, nullptr, qkv, kActNone, s, nullptr, st, eps));
+      SVT_TRY(attend());
+      SVT_TRY(linear(ctx, M, Lw.out, h, h, hb, kActNone, s, st_mid));
+      SVT_TRY(linear(hb, M, Lw.ff1_ln, nullptr, nullptr, mid, kActGelu, s, nullptr, st_mid, eps));
+      SVT_TRY(linear(mid, M, Lw.ff2, h, h, hb, kActNone, s, st));
+    }
+    SVT_TRY(ln_rows(h, e->enc_norm, nullptr, pre, want_stats ? stats_out : nullptr));
+    final_x = pre;
+  } else if (c.stable_layer_norm) {
     // pre-LN layers (HF:612-655) + final encoder LN (HF:792)
     for (int l = 0; l < c.num_layers; ++l) {
       const svt_encoder::Layer& Lw = e->layers[l];
@@ -486,6 +541,7 @@ static int forward_impl(svt_encoder* e, const float* wav, int B, int L, void* ws
   {
     TransformerBuffers tb;
     tb.h = h; tb.hb = hb; tb.qkv = qkv; tb.ctx = ctx; tb.mid = mid; tb.pre = pre;
+    tb.rowstats = reinterpret_cast<float*>(base + p.off_rowstats);
     SVT_TRY(encoder_transformer_forward(e, B, T, Ta, tb, want_stats ? stats_out : nullptr, stats_stride, &final_x, s));
   }
   // ---- A7 whole-tensor output norm + head

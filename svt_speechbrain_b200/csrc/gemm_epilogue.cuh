@@ -21,6 +21,21 @@ struct GemmEpiParams {
   const float* alpha;               // kActPRelu slopes
   const __nv_bfloat16* resid_bf16;  // bf16 residual added BEFORE the activation
   const uint8_t* row_mask;          // rows with mask 0 are written as zeros
+  // LayerNorm folded around the GEMM (pre-LN transformer layers, see GemmArgs):
+  float* row_stats_out;     // producer: [M][N / 128][2] = (sum, sum of squares) of each 128-column slice of the final
+                            // fp32 output rows (plain stores, one writer per slot: deterministic, nothing to zero)
+  const float* ln_stats;    // consumer: [M][K / 128][2] partial statistics of the un-normalised A rows
+  int ln_slots;             // K / 128 (<= kMaxLnSlots)
+  const float* ln_colsum;   // consumer: [N] sums of the (gamma-folded) bf16 weight rows; bias holds beta.W + b
+  float ln_inv_d, ln_eps;   // 1 / (LN width = K), LN epsilon
+};
+
+// What the epilogue fetches one tile ahead of its use.
+constexpr int kMaxLnSlots = 8;
+struct GemmEpiPrefetch {
+  float4 bias;
+  float4 colsum;
+  float4 st[kMaxLnSlots / 2];  // this thread's row: (sum, sumsq) x 2 slots per element
 };
 
 #ifdef __CUDACC__
@@ -46,12 +61,27 @@ __device__ __forceinline__ uint4 epi_lds128(uint32_t addr) {
   return v;
 }
 
-// This warp's slice of the bias for one tile (BN / 2 columns, 4 per lane), fetched one tile ahead of its use.
+// This warp's slice of the bias (and, with a folded LayerNorm, of the weight column sums plus this thread's row
+// statistics) for one tile: BN / 2 columns, 4 per lane, fetched one tile ahead of its use.
 template <int BN>
-__device__ __forceinline__ float4 gemm_load_bias_slice(const GemmEpiParams& p, int col0, int n_valid, int half, int lane) {
+__device__ __forceinline__ GemmEpiPrefetch gemm_epi_prefetch(const GemmEpiParams& p, int row0, int valid, int col0, int n_valid,
+                                                             int quad, int half, int lane) {
+  GemmEpiPrefetch f;
+  f.bias = f.colsum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < kMaxLnSlots / 2; ++i) f.st[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int c = half * (BN / 2) + 4 * lane;
-  if (p.bias == nullptr || 4 * lane >= BN / 2 || c >= n_valid) return make_float4(0.f, 0.f, 0.f, 0.f);
-  return __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c));
+  if (4 * lane < BN / 2 && c < n_valid) {
+    if (p.bias != nullptr) f.bias = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c));
+    if (p.ln_colsum != nullptr) f.colsum = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + c));
+  }
+  if (p.ln_stats != nullptr && quad * 32 + lane < valid) {
+    const float4* st = reinterpret_cast<const float4*>(p.ln_stats + 2 * static_cast<size_t>(row0 + quad * 32 + lane) * p.ln_slots);
+#pragma unroll
+    for (int i = 0; i < kMaxLnSlots / 2; ++i)
+      if (2 * i < p.ln_slots) f.st[i] = st[i];
+  }
+  return f;
 }
 
 // row0 / valid: first output row of this CTA's 128-row tile and how many of its rows exist; col0 / n_valid: first
@@ -68,18 +98,40 @@ __device__ __forceinline__ float4 gemm_load_bias_slice(const GemmEpiParams& p, i
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int row0, int valid, int col0, int n_valid,
                                                    uint32_t tmem_acc, int quad, int half, int lane, uint32_t stage_addr,
-                                                   float4 bias4) {
+                                                   const GemmEpiPrefetch& pf) {
   constexpr int kColsPerWarp = BN / 2;
   const bool f32_path = (p.out_f32 != nullptr || p.resid != nullptr || p.resid_bf16 != nullptr || p.row_mask != nullptr ||
                          p.act == kActPRelu);
   const int c4 = lane & 7;
-  const uint32_t bias_slot = stage_addr + 2048;
+  const uint32_t bias_slot = stage_addr + 2048, colsum_slot = stage_addr + 2048 + 512;
+  const bool ln = p.ln_stats != nullptr;  // host side guarantees !f32_path and bias != nullptr with it
+  float ln_rstd = 1.f, ln_shift = 0.f;
   if (!f32_path && p.bias != nullptr) {
-    if (4 * lane < kColsPerWarp)
-      epi_sts128(bias_slot + 16 * lane, __float_as_uint(bias4.x), __float_as_uint(bias4.y), __float_as_uint(bias4.z),
-                 __float_as_uint(bias4.w));
+    if (4 * lane < kColsPerWarp) {
+      epi_sts128(bias_slot + 16 * lane, __float_as_uint(pf.bias.x), __float_as_uint(pf.bias.y), __float_as_uint(pf.bias.z),
+                 __float_as_uint(pf.bias.w));
+      if (ln)
+        epi_sts128(colsum_slot + 16 * lane, __float_as_uint(pf.colsum.x), __float_as_uint(pf.colsum.y),
+                   __float_as_uint(pf.colsum.z), __float_as_uint(pf.colsum.w));
+    }
     __syncwarp();
   }
+  if (ln) {
+    // y = rstd * (x.W' - mean * colsum) + (beta.W + b): the row statistics were accumulated by the producing GEMM
+    float sum = 0.f, sumsq = 0.f;  // fixed summation order over the slots
+#pragma unroll
+    for (int i = 0; i < kMaxLnSlots / 2; ++i) {
+      sum += pf.st[i].x; sumsq += pf.st[i].y;
+      sum += pf.st[i].z; sumsq += pf.st[i].w;
+    }
+    const float mean = sum * p.ln_inv_d;
+    const float var = fmaxf(sumsq * p.ln_inv_d - mean * mean, 0.f);
+    ln_rstd = rsqrtf(var + p.ln_eps);
+    ln_shift = -mean * ln_rstd;
+  }
+  float ps[8], pss[8];  // producer side: per-lane partial row statistics over this warp's columns
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ps[i] = pss[i] = 0.f;
   // the TMEM read of chunk c + 1 is issued before the math of chunk c and stays in flight under it
   const uint32_t tmem_row = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(half * kColsPerWarp);
   uint32_t rn[32];
@@ -159,6 +211,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
           const size_t off = static_cast<size_t>(row0 + quad * 32 + rr) * static_cast<size_t>(p.ld_out) +
                              static_cast<size_t>(col + 4 * c4);
           if (p.resid != nullptr) { a.x += rs[i].x; a.y += rs[i].y; a.z += rs[i].z; a.w += rs[i].w; }
+          if (p.row_stats_out != nullptr) {
+            ps[i] += (a.x + a.y) + (a.z + a.w);
+            pss[i] = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, pss[i]))));
+          }
           if (p.out_f32 != nullptr) *reinterpret_cast<float4*>(p.out_f32 + off) = a;
           if (p.out_bf16 != nullptr)
             *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
@@ -171,7 +227,17 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rn[j]);
       if (c + 32 < kColsPerWarp) tmem_ld32(tmem_row + c + 32, rn);
-      if (p.bias != nullptr) {
+      if (ln) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 b = epi_lds128(bias_slot + (c + 4 * j) * 4);
+          const uint4 cs = epi_lds128(colsum_slot + (c + 4 * j) * 4);
+          v[4 * j + 0] = fmaf(v[4 * j + 0], ln_rstd, fmaf(ln_shift, __uint_as_float(cs.x), __uint_as_float(b.x)));
+          v[4 * j + 1] = fmaf(v[4 * j + 1], ln_rstd, fmaf(ln_shift, __uint_as_float(cs.y), __uint_as_float(b.y)));
+          v[4 * j + 2] = fmaf(v[4 * j + 2], ln_rstd, fmaf(ln_shift, __uint_as_float(cs.z), __uint_as_float(b.z)));
+          v[4 * j + 3] = fmaf(v[4 * j + 3], ln_rstd, fmaf(ln_shift, __uint_as_float(cs.w), __uint_as_float(b.w)));
+        }
+      } else if (p.bias != nullptr) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint4 b = epi_lds128(bias_slot + (c + 4 * j) * 4);  // same address in every lane: broadcast
@@ -207,6 +273,25 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
                                     static_cast<size_t>(col + 8 * sl)) = o[i];
       }
       __syncwarp();
+    }
+  }
+  if constexpr (BN == 256) {
+    if (p.row_stats_out != nullptr) {
+      // lanes 8r .. 8r + 7 hold partials of row 4i + r over this warp's 128 columns = one slot of that row
+      const int slots = p.ld_out >> 7;
+      const int slot = (col0 >> 7) + half;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          ps[i] += __shfl_xor_sync(0xffffffffu, ps[i], o);
+          pss[i] += __shfl_xor_sync(0xffffffffu, pss[i], o);
+        }
+        const int rr = 4 * i + (lane >> 3);
+        if (c4 == 0 && quad * 32 + rr < valid)
+          *reinterpret_cast<float2*>(p.row_stats_out + 2 * (static_cast<size_t>(row0 + quad * 32 + rr) * slots + slot)) =
+              make_float2(ps[i], pss[i]);
+      }
     }
   }
 }

@@ -240,36 +240,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t stage_mine = smem_u32(stage_area + (warp - kEpiWarp0) * kEpiStageBytes);
     int as = 0;
     uint32_t aphase = 0;
-    float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (blockIdx.x < num_tiles) bias_next = gemm_load_bias_slice<BN>(p.e, (blockIdx.x % p.n_tiles) * p.n_stride, p.n_valid, half, lane);
+    // row0 / valid rows of a tile's output block
+    auto tile_rows = [&](int m_tile, int step, int* row0, int* valid) {
+      if (p.mode == 0) {
+        *row0 = m_tile * BM;
+        *valid = p.M - *row0;
+      } else {
+        const int clip = m_tile / p.tiles_per_clip, tt = m_tile % p.tiles_per_clip;
+        *row0 = clip * p.clip_rows + tt * step;
+        *valid = p.clip_valid - tt * step;
+      }
+    };
+    GemmEpiPrefetch pf_next{};
+    if (blockIdx.x < num_tiles) {
+      int r0, vl;
+      tile_rows(blockIdx.x / p.n_tiles, BM, &r0, &vl);
+      pf_next = gemm_epi_prefetch<BN>(p.e, r0, vl, (blockIdx.x % p.n_tiles) * p.n_stride, p.n_valid, quad, half, lane);
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       int row0, valid;
-      if (p.mode == 0) {
-        row0 = m_tile * BM;
-        valid = p.M - row0;
-      } else {
-        const int clip = m_tile / p.tiles_per_clip;
-        const int tt = m_tile % p.tiles_per_clip;
-        row0 = clip * p.clip_rows + tt * BM;
-        valid = p.clip_valid - tt * BM;
-      }
+      tile_rows(m_tile, BM, &row0, &valid);
       // next tile: its bias slice goes to registers, its residual rows are pulled towards L2
-      const float4 bias_cur = bias_next;
+      const GemmEpiPrefetch pf_cur = pf_next;
       {
-        const int nt = tile + gridDim.x;
-        if (nt < num_tiles) bias_next = gemm_load_bias_slice<BN>(p.e, (nt % p.n_tiles) * p.n_stride, p.n_valid, half, lane);
-      }
-      if (p.e.resid != nullptr) {
         const int nt = tile + gridDim.x;
         if (nt < num_tiles) {
           const int nn = nt % p.n_tiles, nm = nt / p.n_tiles;
           int nrow0, nvalid;
-          if (p.mode == 0) { nrow0 = nm * BM; nvalid = p.M - nrow0; }
-          else { const int cl = nm / p.tiles_per_clip, tt = nm % p.tiles_per_clip, step = p.mode == 2 ? kPosRows : BM;
-                 nrow0 = cl * p.clip_rows + tt * step; nvalid = p.clip_valid - tt * step; }
-          gemm_prefetch_resid<BN>(p.e, nrow0, nvalid, nn * p.n_stride, p.n_valid);
+          tile_rows(nm, p.mode == 2 ? kPosRows : BM, &nrow0, &nvalid);
+          pf_next = gemm_epi_prefetch<BN>(p.e, nrow0, nvalid, nn * p.n_stride, p.n_valid, quad, half, lane);
+          if (p.e.resid != nullptr) gemm_prefetch_resid<BN>(p.e, nrow0, nvalid, nn * p.n_stride, p.n_valid);
         }
       }
       mbar_wait(&tfull_bar[as], aphase);
@@ -281,7 +283,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                               tmem_base + static_cast<uint32_t>(as * BN), quad, half, lane, smem_u32(stage_area), &tempty_bar[as]);
       } else {
         gemm_epilogue_tile<BN>(p.e, row0, valid, n_tile * p.n_stride, p.n_valid, tmem_base + static_cast<uint32_t>(as * BN), quad,
-                               half, lane, stage_mine, bias_cur);
+                               half, lane, stage_mine, pf_cur);
         // all of this warp's TMEM reads are complete (wait::ld above) -> release the accumulator stage
         tc_fence_before();
         __syncwarp();
@@ -375,6 +377,16 @@ int launch(const GemmArgs& g, const KParams& kp, cudaStream_t stream) {
 }  // namespace
 
 int gemm_bf16_tc(const GemmArgs& g, cudaStream_t stream) {
+  if (g.ln_stats != nullptr) {
+    const bool f32_path = g.out_f32 != nullptr || g.resid != nullptr || g.resid_bf16 != nullptr || g.row_mask != nullptr ||
+                          g.act == kActPRelu;
+    if (g.mode != 0 || f32_path || g.bias == nullptr || g.ln_colsum == nullptr || g.out_bf16 == nullptr)
+      return fail(kInvalidArgument, "gemm: a folded LayerNorm needs mode 0, bf16-only output, bias and column sums");
+    if (g.K % 128 != 0 || g.K / 128 > kMaxLnSlots || g.K / 128 % 2 != 0)
+      return fail(kUnsupported, "gemm: a folded LayerNorm needs K in {256, 512, 768, 1024}");
+  }
+  if (g.row_stats_out != nullptr && (g.mode != 0 || g.out_f32 == nullptr || g.N % 256 != 0 || g.ld_out != g.N))
+    return fail(kInvalidArgument, "gemm: row statistics need mode 0, an fp32 output and N % 256 == 0 (= ld_out)");
   if (get_option_gemm_impl() != 1 && gemm_pair_supported(g) && g.M >= 1024 && g.n_taps == 0) return gemm_bf16_tc_pair(g, stream);
   KParams kp{};
   kp.mode = g.mode;
@@ -392,6 +404,9 @@ int gemm_bf16_tc(const GemmArgs& g, cudaStream_t stream) {
   kp.e.alpha = g.alpha;
   kp.e.resid_bf16 = g.resid_bf16;
   kp.e.row_mask = g.row_mask;
+  kp.e.row_stats_out = g.row_stats_out;
+  kp.e.ln_stats = g.ln_stats; kp.e.ln_colsum = g.ln_colsum;
+  kp.e.ln_slots = g.K / 128; kp.e.ln_inv_d = 1.0f / static_cast<float>(g.K); kp.e.ln_eps = g.ln_eps;
   if (g.act == kActPRelu && g.alpha == nullptr) return fail(kInvalidArgument, "gemm: PReLU needs per-column slopes");
   kp.n_taps = 0;
   if (g.n_taps > 0) {

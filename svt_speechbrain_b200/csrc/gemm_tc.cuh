@@ -45,6 +45,15 @@ struct GemmArgs {
   const float* alpha = nullptr;            // [N] per-column slope for kActPRelu
   const __nv_bfloat16* resid_bf16 = nullptr;  // bf16 residual [rows, ld_out] added before the activation (ResNet blocks)
   const uint8_t* row_mask = nullptr;       // [rows]: rows with mask 0 are written as zeros (padding ring of a feature map)
+  // LayerNorm folded around the GEMM (pre-LN transformer layers).  The GEMM that PRODUCES the residual stream adds
+  // (sum, sum of squares) of every 128-column slice of its output rows to row_stats_out [M][N / 128][2] (one writer
+  // per slot, so deterministic and nothing to zero); the GEMM that CONSUMES LN(x) (ln_stats, same layout) multiplies the
+  // un-normalised bf16 rows by W' = gamma o W and finishes y = rstd * (x.W' - mean * colsum) + bias in its epilogue,
+  // with colsum[n] = sum_k W'[n][k] and bias[n] = beta.W[n] + b[n] (bf16-only outputs, LN width = K).
+  float* row_stats_out = nullptr;
+  const float* ln_stats = nullptr;
+  const float* ln_colsum = nullptr;
+  float ln_eps = 1e-5f;
   // ---- shifted-row taps (linear mode only): k-block kb reads A rows (row + tap_off[kb / (k_inner / 64)]), columns
   // (kb % (k_inner / 64)) * 64 .. + 64; K = n_taps * k_inner.  This is a 2-D convolution over feature maps stored as
   // flat rows [frame][y][x] with a zero padding ring: tap (dy, dx) is the constant row offset dy * W_padded + dx.

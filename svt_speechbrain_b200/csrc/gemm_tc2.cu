@@ -195,8 +195,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quad = warp & 3;
     const int half = (warp - kEpiWarp0) >> 2;
     const uint32_t stage_mine = smem_u32(stage_area + (warp - kEpiWarp0) * kEpiStageBytes);
-    float4 bias_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pair < num_tiles) bias_next = gemm_load_bias_slice<BN2>(p, (pair % n_tiles) * BN2, BN2, half, lane);
+    GemmEpiPrefetch pf_next{};
+    if (pair < num_tiles) {
+      const int r0 = ((pair / n_tiles) * 2 + static_cast<int>(rank)) * BM;
+      pf_next = gemm_epi_prefetch<BN2>(p, r0, p.M - r0, (pair % n_tiles) * BN2, BN2, quad, half, lane);
+    }
     const uint32_t leader_tempty0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     int as = 0;
     uint32_t aphase = 0;
@@ -204,19 +207,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int n_tile = tile % n_tiles;
       const int row0 = ((tile / n_tiles) * 2 + static_cast<int>(rank)) * BM;
       const int valid = p.M - row0;
-      const float4 bias_cur = bias_next;
-      if (tile + num_pairs < num_tiles) bias_next = gemm_load_bias_slice<BN2>(p, ((tile + num_pairs) % n_tiles) * BN2, BN2, half, lane);
-      if (p.resid != nullptr) {
+      const GemmEpiPrefetch pf_cur = pf_next;
+      {
         const int nt = tile + num_pairs;
         if (nt < num_tiles) {
           const int nrow0 = ((nt / n_tiles) * 2 + static_cast<int>(rank)) * BM;
-          gemm_prefetch_resid<BN2>(p, nrow0, p.M - nrow0, (nt % n_tiles) * BN2, BN2);
+          pf_next = gemm_epi_prefetch<BN2>(p, nrow0, p.M - nrow0, (nt % n_tiles) * BN2, BN2, quad, half, lane);
+          if (p.resid != nullptr) gemm_prefetch_resid<BN2>(p, nrow0, p.M - nrow0, (nt % n_tiles) * BN2, BN2);
         }
       }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       gemm_epilogue_tile<BN2>(p, row0, valid, n_tile * BN2, BN2, tmem_base + static_cast<uint32_t>(as * BN2), quad, half, lane,
-                              stage_mine, bias_cur);
+                              stage_mine, pf_cur);
       // all of this warp's TMEM reads are complete -> release the accumulator stage to the leader's MMA thread
       tc_fence_before();
       __syncwarp();
@@ -246,6 +249,8 @@ int gemm_bf16_tc_pair(const GemmArgs& g, cudaStream_t stream) {
   GemmEpiParams p{};
   p.M = g.M; p.bias = g.bias; p.resid = g.resid; p.out_f32 = g.out_f32; p.out_bf16 = g.out_bf16;
   p.ld_out = g.ld_out; p.act = g.act; p.alpha = g.alpha; p.resid_bf16 = g.resid_bf16; p.row_mask = g.row_mask;
+  p.row_stats_out = g.row_stats_out; p.ln_stats = g.ln_stats; p.ln_colsum = g.ln_colsum;
+  p.ln_slots = g.K / 128; p.ln_inv_d = 1.0f / static_cast<float>(g.K); p.ln_eps = g.ln_eps;
   const int k_inner = g.k_inner > 0 ? g.k_inner : g.K;
   CUtensorMap tmA, tmB;
   const uint32_t abox[3] = {BK, 1, BM};

@@ -51,6 +51,7 @@ struct LinearW {
   __nv_bfloat16* w = nullptr;  // [N, K]
   float* b = nullptr;          // [N]
   int N = 0, K = 0;
+  float* colsum = nullptr;     // [N], LayerNorm-folded weights only (GemmArgs::ln_colsum); b then holds beta.W + b
 };
 struct NormW {
   float* g = nullptr;
@@ -67,8 +68,10 @@ int pack_posconv_weight(const float* w_dev, const float* tap_scale, int D, int g
 
 namespace svt {
 // scratch of the shared transformer body (rows M = clips * Ta): h fp32 [M, D] residual stream (in / out), hb bf16 copy
-// [M, D] (in), qkv bf16 [M, 3D], ctx bf16 [M, D], mid bf16 [M, F], pre fp32 [M, D]
+// [M, D] (in), qkv bf16 [M, 3D], ctx bf16 [M, D], mid bf16 [M, F], pre fp32 [M, D], rowstats fp32
+// transformer_rowstats_bytes() (per-row sum / sum of squares links of the folded-LayerNorm chain)
 struct TransformerBuffers {
+  float* rowstats = nullptr;
   float* h = nullptr;
   __nv_bfloat16* hb = nullptr;
   __nv_bfloat16* qkv = nullptr;
@@ -104,6 +107,7 @@ struct svt_encoder {
   struct Layer {
     svt::NormW ln1, ln2;
     svt::LinearW qkv, out, ff1, ff2;
+    svt::LinearW qkv_ln, ff1_ln;  // pre-LN models: gamma / beta of ln1 / ln2 folded in (option "ln_fold")
   };
   std::vector<Layer> layers;
   float* head_w = nullptr;  // [n_out, D] fp32
@@ -117,6 +121,7 @@ struct svt_encoder {
 
 namespace svt {
 int encoder_finalize(svt_encoder* e);
+size_t transformer_rowstats_bytes(const svt_encoder* e, size_t M);
 int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, const TransformerBuffers& tb, double* stats_out,
                                 int stats_stride, const float** final_x_out, cudaStream_t s);
 }  // namespace svt

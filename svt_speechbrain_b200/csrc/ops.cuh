@@ -19,6 +19,7 @@ int attention_bf16(const AttentionArgs& a, cudaStream_t stream);       // dispat
 int attention_bf16_tc(const AttentionArgs& a, cudaStream_t stream);    // tcgen05 / TMEM kernel (attention_tc.cu), head_dim 64
 // process-wide options (svt_set_option): "attention_impl" 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 kernel
 int get_option_attention_impl();
+int get_option_ln_fold();
 // development aid: device buffer of 4 x 256 int64 clock stamps written by CTA 0 of the tcgen05 attention kernel
 void set_attention_trace_buffer(long long* dev_ptr);
 
@@ -41,6 +42,11 @@ struct LayerNormArgs {
   int stats_stride = 0;
 };
 int layer_norm(const LayerNormArgs& a, cudaStream_t stream);
+// Folded-LayerNorm helpers (GemmArgs::ln_stats): y = bf16(x) plus per-row (sum, sum of squares) -> stats [rows][2];
+// and the per-feature vectors of a folded weight: colsum[n] = sum_k w_packed[n][k], bias[n] += scale * w_f32[n].beta
+int row_stats_cast(const float* x, int rows, int D, __nv_bfloat16* y, float* stats, cudaStream_t stream);
+int ln_fold_vectors(const float* w_f32, const __nv_bfloat16* w_packed, const float* beta, float scale, int N, int K,
+                    float* colsum, float* bias, cudaStream_t stream);
 
 // sum / sum of squares of an fp32 tensor (whole-tensor layer norm, huggingface_interface.py:289)
 int tensor_stats(const float* x, size_t n, double* stats /*[2], zeroed here*/, cudaStream_t stream);

@@ -388,6 +388,48 @@ __global__ void weight_norm_scale_kernel(const float* __restrict__ v, const floa
   if (threadIdx.x == 0) out[j] = static_cast<float>(static_cast<double>(g[j]) / sqrt(tot));
 }
 
+// one warp per row: y = bf16(x) and (sum, sum of squares) of every 128-column slice of the fp32 row -- the first link
+// of the folded-LayerNorm chain in the layout of GemmArgs::row_stats_out (later links come out of GEMM epilogues)
+__global__ void row_stats_cast_kernel(const float* __restrict__ x, int rows, int D, __nv_bfloat16* __restrict__ y,
+                                      float* __restrict__ stats) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+  const int slots = D / 128;
+  for (int j = 0; j < slots; ++j) {  // one pass of the warp = one 128-column slot
+    const float4 v = xr[j * 32 + lane];
+    float s = (v.x + v.y) + (v.z + v.w);
+    float ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+    yr[j * 32 + lane] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    if (lane == 0) *reinterpret_cast<float2*>(stats + 2 * (static_cast<size_t>(row) * slots + j)) = make_float2(s, ss);
+  }
+}
+
+// one warp per output feature n: colsum[n] = sum_k float(w_packed[n][k]) (what the tensor cores multiply the row mean
+// by), bias[n] += scale * sum_k w_f32[n][k] * beta[k]
+__global__ void ln_fold_vectors_kernel(const float* __restrict__ w_f32, const __nv_bfloat16* __restrict__ w_packed,
+                                       const float* __restrict__ beta, float scale, int N, int K,
+                                       float* __restrict__ colsum, float* __restrict__ bias) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float cs = 0.f, d = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    cs += __bfloat162float(w_packed[static_cast<size_t>(n) * K + k]);
+    d = fmaf(w_f32[static_cast<size_t>(n) * K + k], beta[k], d);
+  }
+  cs = warp_sum(cs);
+  d = warp_sum(d);
+  if (lane == 0) {
+    colsum[n] = cs;
+    bias[n] += scale * d;
+  }
+}
+
 template <typename F>
 int dispatch_nv(int D, F&& f) {
   switch (D / 128) {
@@ -415,6 +457,21 @@ int layer_norm(const LayerNormArgs& a, cudaStream_t stream) {
     SVT_POST_LAUNCH();
     return static_cast<int>(kOk);
   });
+}
+
+int row_stats_cast(const float* x, int rows, int D, __nv_bfloat16* y, float* stats, cudaStream_t stream) {
+  if (rows <= 0) return kOk;
+  if (D % 128 != 0) return fail(kInvalidArgument, "row_stats_cast: D % 128 != 0");
+  row_stats_cast_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(x, rows, D, y, stats);
+  SVT_POST_LAUNCH();
+  return kOk;
+}
+
+int ln_fold_vectors(const float* w_f32, const __nv_bfloat16* w_packed, const float* beta, float scale, int N, int K,
+                    float* colsum, float* bias, cudaStream_t stream) {
+  ln_fold_vectors_kernel<<<ceil_div(N, 8), 256, 0, stream>>>(w_f32, w_packed, beta, scale, N, K, colsum, bias);
+  SVT_POST_LAUNCH();
+  return kOk;
 }
 
 int tensor_stats(const float* x, size_t n, double* stats, cudaStream_t stream) {

@@ -310,7 +310,7 @@ int finalize_video(svt_video* v) {
 
 struct VideoPlan {
   int B, T, Ta, N;
-  size_t off_stats, off_col, off_f0, off_buf[4], off_mask[4], off_cat, off_h, off_hb, off_qkv, off_ctx, off_mid, off_pre, total;
+  size_t off_stats, off_col, off_f0, off_buf[4], off_mask[4], off_cat, off_h, off_hb, off_qkv, off_ctx, off_mid, off_pre, off_rowstats, total;
   size_t buf_elems;
 };
 VideoPlan make_plan(const svt_video* v, int B, int T) {
@@ -332,6 +332,7 @@ VideoPlan make_plan(const svt_video* v, int B, int T) {
   p.off_ctx = take(N * D * 2);
   p.off_mid = take(N * F * 2);
   p.off_pre = take(N * D * 4);
+  p.off_rowstats = take(transformer_rowstats_bytes(v->enc, N));
   p.total = off;
   return p;
 }
@@ -451,6 +452,7 @@ int forward_video(svt_video* v, const float* video, int B, int T, void* ws, size
   tb.ctx = reinterpret_cast<__nv_bfloat16*>(base + p.off_ctx);
   tb.mid = reinterpret_cast<__nv_bfloat16*>(base + p.off_mid);
   tb.pre = reinterpret_cast<float*>(base + p.off_pre);
+  tb.rowstats = reinterpret_cast<float*>(base + p.off_rowstats);
   {
     GemmArgs g;
     g.a = cat;

@@ -223,3 +223,30 @@ def test_transcribe_songs_pools_utterances_across_songs():
     assert len(pooled) == 3
     for a, b in zip(pooled, one_by_one):
         assert a.shape == b.shape and np.allclose(a, b)
+
+
+def test_folded_layer_norm_matches_separate_kernels():
+    """Option "ln_fold": the pre-LN layers' LayerNorms folded into the GEMMs (default) vs run as separate kernels --
+    same logits within the bf16 noise of either path, and both within tolerance of the oracle."""
+    from oracle import make_golden as mg
+    from oracle import wav2vec2_oracle as wo
+    import svt_speechbrain_b200 as svt
+    from svt_speechbrain_b200._lib import check, lib
+
+    cfg = wo.W2V2Config.large()
+    lobe, lin, sd, head = _build(cfg)
+    tr = svt.AMTTranscriber(lobe, lin)
+    wav = mg.synth_wav(2, 24000, seed=11)
+    with torch.no_grad():
+        ref = wo.amt_logits(cfg, sd, head, wav).numpy()
+    try:
+        check(lib().svt_set_option(b"ln_fold", 0))
+        sep = tr.logits(wav.cuda()).cpu()
+        check(lib().svt_set_option(b"ln_fold", 1))
+        fold = tr.logits(wav.cuda()).cpu()
+    finally:
+        lib().svt_set_option(b"ln_fold", 1)
+    _check_logits(sep, ref, "separate LayerNorm kernels")
+    _check_logits(fold, ref, "folded LayerNorm")
+    assert float((sep - fold).abs().max()) > 0.0   # the two paths really are different code
+    assert float((sep - fold).abs().max()) < 5e-2

@@ -131,3 +131,57 @@ def test_posconv(D, groups, T, Ta, B, impl, taps):
     print(f"posconv D={D} T={T}: max abs err {err:.3e}")
     assert err < 3e-3
     assert torch.equal(out[:, T:], resid[:, T:])  # padding rows untouched
+
+
+@pytest.mark.parametrize("M,D,N,act,offset", [(515, 1024, 512, 0, 0.0), (2048, 1024, 3072, 0, 0.5), (1500, 1024, 4096, 1, -1.0),
+                                              (300, 512, 256, 1, 3.0)])
+def test_gemm_folded_layer_norm_chain(M, D, N, act, offset):
+    """producer GEMM (+residual, row statistics, bf16 copy) -> consumer GEMM with the LayerNorm folded in ==
+    LayerNorm(h) @ W^T + b of the same fp32 rows (option "ln_fold", encoder.cu)."""
+    from gpu_util import rel_l2
+    from svt_speechbrain_b200._lib import check, current_stream_ptr, lib, ptr
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    K0 = 256
+    a = torch.randn(M, K0, device="cuda", generator=g).bfloat16()
+    w0 = (torch.randn(D, K0, device="cuda", generator=g) / K0 ** 0.5).bfloat16()
+    b0 = torch.randn(D, device="cuda", generator=g)
+    resid = torch.randn(M, D, device="cuda", generator=g) * (1 + torch.rand(M, 1, device="cuda", generator=g) * 4) + offset
+    gamma = 1 + 0.3 * torch.randn(D, device="cuda", generator=g)
+    beta = 0.2 * torch.randn(D, device="cuda", generator=g)
+    w1 = torch.randn(N, D, device="cuda", generator=g) / D ** 0.5
+    b1 = torch.randn(N, device="cuda", generator=g)
+    eps = 1e-5
+    # producer
+    h = resid.clone()
+    hb = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    stats = torch.full((M, D // 128, 2), float("nan"), device="cuda")  # every slot has exactly one writer
+    check(lib().svt_op_gemm_ln(ptr(a), ptr(w0), ptr(b0), None, None, 0.0, ptr(stats), ptr(h), ptr(h), ptr(hb), M, D, K0, 0,
+                               current_stream_ptr()))
+    h_ref = a.float() @ w0.float().t() + b0 + resid
+    assert (h - h_ref).abs().max().item() < 2e-3
+    assert torch.equal(hb, h.bfloat16())
+    hs = h.view(M, D // 128, 128)
+    assert torch.allclose(stats[:, :, 0], hs.sum(2), rtol=1e-4, atol=2e-3)
+    assert torch.allclose(stats[:, :, 1], (hs * hs).sum(2), rtol=1e-4, atol=2e-3)
+    # row_stats_cast: the first link of the chain
+    hb2 = torch.empty_like(hb)
+    stats2 = torch.empty_like(stats)
+    check(lib().svt_op_row_stats_cast(ptr(h), M, D, ptr(hb2), ptr(stats2), current_stream_ptr()))
+    assert torch.equal(hb2, hb) and torch.allclose(stats2, stats, rtol=1e-4, atol=2e-3)
+    # consumer: weights folded on the host exactly like encoder_finalize does on the device
+    wf = (w1 * gamma[None, :]).bfloat16()
+    colsum = wf.float().sum(1)
+    d = b1 + w1 @ beta
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    check(lib().svt_op_gemm_ln(ptr(hb), ptr(wf), ptr(d), ptr(colsum), ptr(stats), eps, None, None, None, ptr(out), M, N, D, act,
+                               current_stream_ptr()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(h, (D,), gamma, beta, eps) @ w1.t() + b1
+    # the unfused path: normalised rows rounded to bf16, bf16 weights
+    unf = torch.nn.functional.layer_norm(h, (D,), gamma, beta, eps).bfloat16().float() @ w1.bfloat16().float().t() + b1
+    if act == 1:
+        ref, unf = torch.nn.functional.gelu(ref), torch.nn.functional.gelu(unf)
+    e_fold, e_unf = rel_l2(out.float(), ref), rel_l2(unf.bfloat16().float(), ref)
+    print(f"folded LN M={M} D={D} N={N} offset={offset}: rel-L2 folded {e_fold:.3e} vs separate-LN {e_unf:.3e}")
+    assert torch.isfinite(out.float()).all()
+    assert e_fold < 1e-2 and e_fold < 3 * e_unf + 1e-3

@@ -77,6 +77,11 @@ typedef struct svt_encoder_config {
   float layer_norm_eps;    /* 1e-5 */
   int normalize_wav;       /* lobe.normalize_wav: F.layer_norm(wav, wav.shape), huggingface_interface.py:288-289 */
   int output_norm;         /* lobe.output_norm:  F.layer_norm(out, out.shape),  huggingface_interface.py:295-296 */
+  int feat_proj_norm;      /* 1: LayerNorm before the feature projection (wav2vec2, HuBERT large); 0: none (HuBERT base,
+                              HubertConfig.feat_proj_layer_norm = False) */
+  int pos_conv_layers;     /* 0: one weight-normed grouped conv + GELU (wav2vec2, HuBERT).  n > 0: data2vec-audio's stack
+                              of n [grouped conv (kernel pos_conv_kernel, plain weights) -> LayerNorm without affine ->
+                              GELU] (Data2VecAudioPositionalConvEmbedding; n = 5, kernel 19) */
 } svt_encoder_config;
 
 int svt_encoder_create(const svt_encoder_config* cfg, svt_encoder** out);

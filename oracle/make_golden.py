@@ -94,8 +94,8 @@ def random_frames(n, seed, p_hi=0.5):
 
 
 def _ref_lobe_with(cfg: W2V2Config, sd, tmp):
-    d = os.path.join(tmp, f"wav2vec2-{abs(hash(str(cfg))) % 10**8}")
-    rb.make_offline_model_dir(d, cfg.hf_kwargs(), seed=0)
+    d = os.path.join(tmp, f"{cfg.family}-{abs(hash(str(cfg))) % 10**8}")
+    rb.make_offline_model_dir(d, cfg.hf_kwargs(), seed=0, family=cfg.family)
     lobe = rb.reference_lobe(d, output_norm=True)
     missing = lobe.load_state_dict(sd, strict=True)
     return lobe
@@ -124,6 +124,18 @@ def gold_w2v2(name, cfg, B, L, tmp, store_weights, taps_keep=8):
             out["head/" + k] = v.numpy()
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
     print(name, "logits", tuple(logits.shape), "absmax", float(logits.abs().max()))
+
+
+def gold_hubert(tmp):
+    """HuBERT through the same reference lobe (source path contains "hubert" -> HubertModel): base = group norm,
+    post-LN layers, NO LayerNorm in the feature projection; large = wav2vec2-large's graph."""
+    gold_w2v2("hubert_base_1s", W2V2Config.hubert_base(), B=2, L=16000, tmp=tmp, store_weights=False)
+    gold_w2v2("hubert_large_1s", W2V2Config.hubert_large(), B=1, L=16000, tmp=tmp, store_weights=False)
+
+
+def gold_data2vec(tmp):
+    """data2vec-audio through the reference lobe (source path contains "data2vec" -> Data2VecAudioModel)."""
+    gold_w2v2("data2vec_base_1s", W2V2Config.data2vec_base(), B=2, L=16000, tmp=tmp, store_weights=False)
 
 
 def gold_fusion(name, D, d_ffn, nhead, B, Ta, Tv, store_weights):
@@ -204,6 +216,8 @@ def main():
         gold_w2v2("w2v2_large_1s", W2V2Config.large(), B=2, L=16000, tmp=tmp, store_weights=False)
         gold_w2v2("w2v2_base_1s", W2V2Config.base(), B=2, L=16000, tmp=tmp, store_weights=False)
         gold_w2v2("w2v2_large_5s", W2V2Config.large(), B=1, L=80000, tmp=tmp, store_weights=False)
+        gold_hubert(tmp)
+        gold_data2vec(tmp)
     gold_fusion("fusion_tiny", D=64, d_ffn=96, nhead=4, B=2, Ta=13, Tv=15, store_weights=True)
     gold_fusion("fusion_full", D=1024, d_ffn=3072, nhead=8, B=1, Ta=49, Tv=50, store_weights=False)
     gold_fusion("fusion_full_pad", D=1024, d_ffn=3072, nhead=8, B=2, Ta=49, Tv=45, store_weights=False)

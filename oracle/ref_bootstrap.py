@@ -46,15 +46,22 @@ def setup_paths():
             sys.path.insert(0, p)
 
 
-def make_offline_model_dir(path, config_kwargs, seed=0):
-    """Random-init HF Wav2Vec2Model + feature extractor saved under `path`."""
+def make_offline_model_dir(path, config_kwargs, seed=0, family="wav2vec2"):
+    """Random-init HF Wav2Vec2Model / HubertModel + feature extractor saved under `path` (the reference picks the
+    HF class by substring of the path, huggingface_interface.py:108-119)."""
     import torch
-    from transformers import Wav2Vec2Config, Wav2Vec2FeatureExtractor, Wav2Vec2Model
+    from transformers import (Data2VecAudioConfig, Data2VecAudioModel, HubertConfig, HubertModel, Wav2Vec2Config,
+                              Wav2Vec2FeatureExtractor, Wav2Vec2Model)
 
-    assert "wav2vec2" in path
+    assert family in path
     os.makedirs(path, exist_ok=True)
     torch.manual_seed(seed)
-    Wav2Vec2Model(Wav2Vec2Config(**config_kwargs)).save_pretrained(path)
+    if family == "hubert":
+        HubertModel(HubertConfig(**config_kwargs)).save_pretrained(path)
+    elif family == "data2vec":
+        Data2VecAudioModel(Data2VecAudioConfig(**config_kwargs)).save_pretrained(path)
+    else:
+        Wav2Vec2Model(Wav2Vec2Config(**config_kwargs)).save_pretrained(path)
     Wav2Vec2FeatureExtractor(
         feature_size=1, sampling_rate=16000, padding_value=0.0, do_normalize=True, return_attention_mask=True
     ).save_pretrained(path)

@@ -47,6 +47,27 @@ class W2V2Config:
     num_conv_pos_embeddings: int = 128
     num_conv_pos_embedding_groups: int = 16
     layer_norm_eps: float = 1e-5
+    # HuBERT (HF modeling_hubert.py, HubertFeatureProjection): base checkpoints project the conv features without the
+    # LayerNorm that wav2vec2 and HuBERT-large apply first.  family picks the HF classes (reference :108-119).
+    feat_proj_layer_norm: bool = True
+    family: str = "wav2vec2"
+    # data2vec-audio (HF modeling_data2vec_audio.py): the positional embedding is a stack of num_conv_pos_embeddings
+    # (5) layers of [grouped conv k = conv_pos_kernel_size (19) -> LayerNorm without affine -> GELU], no weight norm.
+    conv_pos_kernel_size: int = 19
+
+    @staticmethod
+    def data2vec_base() -> "W2V2Config":
+        return W2V2Config(family="data2vec", feat_extract_norm="layer", num_conv_pos_embeddings=5)
+
+    @staticmethod
+    def hubert_base() -> "W2V2Config":
+        return W2V2Config(family="hubert", feat_proj_layer_norm=False)
+
+    @staticmethod
+    def hubert_large() -> "W2V2Config":
+        c = W2V2Config.large()
+        c.family = "hubert"
+        return c
 
     @staticmethod
     def large() -> "W2V2Config":
@@ -80,10 +101,17 @@ class W2V2Config:
             num_conv_pos_embeddings=cfg.num_conv_pos_embeddings,
             num_conv_pos_embedding_groups=cfg.num_conv_pos_embedding_groups,
             layer_norm_eps=cfg.layer_norm_eps,
+            feat_proj_layer_norm=bool(getattr(cfg, "feat_proj_layer_norm", True)),
+            family={"Hub": "hubert", "Dat": "data2vec"}.get(type(cfg).__name__[:3], "wav2vec2"),
+            conv_pos_kernel_size=int(getattr(cfg, "conv_pos_kernel_size", 19)),
         )
 
     def hf_kwargs(self) -> dict:
+        extra = {"feat_proj_layer_norm": self.feat_proj_layer_norm} if self.family == "hubert" else {}
+        if self.family == "data2vec":
+            extra = {"conv_pos_kernel_size": self.conv_pos_kernel_size}
         return dict(
+            **extra,
             hidden_size=self.hidden_size,
             num_hidden_layers=self.num_hidden_layers,
             num_attention_heads=self.num_attention_heads,
@@ -187,13 +215,27 @@ def encoder(cfg: W2V2Config, sd, h, prefix="model.", taps: Optional[dict] = None
     """HF:658-727 (base, post-LN) / HF:730-803 (large, stable-LN)."""
     eps = cfg.layer_norm_eps
     e = prefix + "encoder."
-    w = pos_conv_weight(sd, prefix)
-    kpos = cfg.num_conv_pos_embeddings
-    pos = F.conv1d(h.transpose(1, 2), w, sd[e + "pos_conv_embed.conv.bias"], padding=kpos // 2,
-                   groups=cfg.num_conv_pos_embedding_groups)
-    if kpos % 2 == 0:
-        pos = pos[:, :, :-1]  # HF:371-379 SamePad
-    pos = gelu(pos).transpose(1, 2)
+    if cfg.family == "data2vec":
+        # Data2VecAudioPositionalConvEmbedding: 5 x [conv -> SamePad -> LN(no affine) -> GELU], then h + pos
+        kpos = cfg.conv_pos_kernel_size
+        pos = h.transpose(1, 2)
+        for i in range(cfg.num_conv_pos_embeddings):
+            lp = f"{e}pos_conv_embed.layers.{i}.conv."
+            pos = F.conv1d(pos, sd[lp + "weight"], sd[lp + "bias"], padding=kpos // 2,
+                           groups=cfg.num_conv_pos_embedding_groups)
+            if kpos % 2 == 0:
+                pos = pos[:, :, :-1]
+            pos = F.layer_norm(pos.transpose(1, 2), (pos.shape[1],), None, None, 1e-5).transpose(1, 2)
+            pos = gelu(pos)
+        pos = pos.transpose(1, 2)
+    else:
+        w = pos_conv_weight(sd, prefix)
+        kpos = cfg.num_conv_pos_embeddings
+        pos = F.conv1d(h.transpose(1, 2), w, sd[e + "pos_conv_embed.conv.bias"], padding=kpos // 2,
+                       groups=cfg.num_conv_pos_embedding_groups)
+        if kpos % 2 == 0:
+            pos = pos[:, :, :-1]  # HF:371-379 SamePad
+        pos = gelu(pos).transpose(1, 2)
     h = h + pos
     if taps is not None:
         taps["pos"] = h
@@ -221,7 +263,8 @@ def lobe_forward(cfg: W2V2Config, sd, wav: torch.Tensor, normalize_wav=True, out
     if normalize_wav:
         x = whole_tensor_layer_norm(x)
     h = feature_encoder(cfg, sd, x, prefix, taps).transpose(1, 2)  # HF:1349
-    h = _ln(sd, h, prefix + "feature_projection.layer_norm.", cfg.layer_norm_eps)
+    if cfg.feat_proj_layer_norm:  # HF wav2vec2:1352 / hubert HubertFeatureProjection.forward
+        h = _ln(sd, h, prefix + "feature_projection.layer_norm.", cfg.layer_norm_eps)
     h = F.linear(h, sd[prefix + "feature_projection.projection.weight"], sd[prefix + "feature_projection.projection.bias"])
     if taps is not None:
         taps["proj"] = h
@@ -269,8 +312,14 @@ def random_weights(cfg: W2V2Config, seed: int = 0) -> Dict[str, torch.Tensor]:
     """Random-init weights of the named architecture via HF's own `_init_weights`
     (transformers is a dependency of the reference and exists on the GPU box too).
     Returns the lobe-style state dict (prefix "model.")."""
-    from transformers import Wav2Vec2Config, Wav2Vec2Model
+    from transformers import (Data2VecAudioConfig, Data2VecAudioModel, HubertConfig, HubertModel, Wav2Vec2Config,
+                              Wav2Vec2Model)
 
     torch.manual_seed(seed)
-    m = Wav2Vec2Model(Wav2Vec2Config(**cfg.hf_kwargs())).eval()
+    if cfg.family == "hubert":
+        m = HubertModel(HubertConfig(**cfg.hf_kwargs())).eval()
+    elif cfg.family == "data2vec":
+        m = Data2VecAudioModel(Data2VecAudioConfig(**cfg.hf_kwargs())).eval()
+    else:
+        m = Wav2Vec2Model(Wav2Vec2Config(**cfg.hf_kwargs())).eval()
     return {"model." + k: v.detach().clone().float() for k, v in m.state_dict().items()}

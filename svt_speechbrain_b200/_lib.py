@@ -17,7 +17,8 @@ class EncoderConfig(C.Structure):
         ("conv_kernel", C.c_int * MAX_CONV_LAYERS), ("conv_stride", C.c_int * MAX_CONV_LAYERS),
         ("conv_bias", C.c_int), ("feat_norm_layer", C.c_int), ("stable_layer_norm", C.c_int),
         ("pos_conv_kernel", C.c_int), ("pos_conv_groups", C.c_int), ("layer_norm_eps", C.c_float),
-        ("normalize_wav", C.c_int), ("output_norm", C.c_int),
+        ("normalize_wav", C.c_int), ("output_norm", C.c_int), ("feat_proj_norm", C.c_int),
+        ("pos_conv_layers", C.c_int),
     ]
 
 

@@ -200,13 +200,48 @@ int svt::encoder_finalize(svt_encoder* e) {
     if (c.feat_norm_layer) SVT_TRY(pack_norm(pool, reg, p + "layer_norm.", C, &nw));
     e->conv_norm.push_back(nw);
   }
-  SVT_TRY(pack_norm(pool, reg, "feature_projection.layer_norm.", C, &e->proj_norm));
+  if (c.feat_proj_norm) SVT_TRY(pack_norm(pool, reg, "feature_projection.layer_norm.", C, &e->proj_norm));
   SVT_TRY(pack_linear(pool, reg, "feature_projection.projection.", D, C, &e->proj));
   }  // !transformer_only
 
-  // positional conv: weight-norm recomposition folded here (HF:343-355), packed per (group, tap)
-  {
+  // positional conv weights packed per (group, tap): dst[g][j][co][ci] = v[g*Dg+co][ci][j] * scale[j]
+  auto pack_pos = [&](const RawTensor* v, const float* scale, __nv_bfloat16** dst) -> int {
     const int G = c.pos_conv_groups, taps = c.pos_conv_kernel, Dg = D / G;
+    SVT_TRY(pool.alloc_t<__nv_bfloat16>(static_cast<size_t>(G) * taps * 64 * 64, dst));
+    SVT_CUDA(cudaMemset(*dst, 0, sizeof(__nv_bfloat16) * static_cast<size_t>(G) * taps * 64 * 64));
+    if (Dg == 64) return pack_posconv_weight(v->dev, scale, D, G, taps, *dst, 0);
+    // generic (base: Dg = 48): build on the host, small one-time cost
+    std::vector<float> hv(v->numel()), hs(taps, 1.f);
+    SVT_CUDA(cudaMemcpy(hv.data(), v->dev, sizeof(float) * hv.size(), cudaMemcpyDeviceToHost));
+    if (scale != nullptr) SVT_CUDA(cudaMemcpy(hs.data(), scale, sizeof(float) * taps, cudaMemcpyDeviceToHost));
+    std::vector<__nv_bfloat16> hp(static_cast<size_t>(G) * taps * 64 * 64, __float2bfloat16(0.f));
+    for (int gi = 0; gi < G; ++gi)
+      for (int j = 0; j < taps; ++j)
+        for (int co = 0; co < Dg; ++co)
+          for (int ci = 0; ci < Dg; ++ci)
+            hp[((static_cast<size_t>(gi) * taps + j) * 64 + co) * 64 + ci] =
+                __float2bfloat16(hv[(static_cast<size_t>(gi * Dg + co) * Dg + ci) * taps + j] * hs[j]);
+    SVT_CUDA(cudaMemcpy(*dst, hp.data(), sizeof(__nv_bfloat16) * hp.size(), cudaMemcpyHostToDevice));
+    return kOk;
+  };
+  e->pos_stack.clear();
+  if (c.pos_conv_layers > 0) {
+    // data2vec-audio: plain conv weights, one set per stacked layer (HF Data2VecAudioPositionalConvLayer)
+    const int taps = c.pos_conv_kernel, Dg = D / c.pos_conv_groups;
+    for (int i = 0; i < c.pos_conv_layers; ++i) {
+      const std::string pc = "encoder.pos_conv_embed.layers." + std::to_string(i) + ".conv.";
+      const RawTensor* w;
+      SVT_TRY(reg.require(pc + "weight", {D, Dg, taps}, &w));
+      svt_encoder::PosLayer pl;
+      SVT_TRY(pack_pos(w, nullptr, &pl.w));
+      SVT_TRY(pack_vec(pool, reg, pc + "bias", D, 1.f, &pl.b));
+      e->pos_stack.push_back(pl);
+    }
+    SVT_TRY(zero_vec(pool, D, 1.f, &e->ones));
+    SVT_TRY(zero_vec(pool, D, 0.f, &e->zeros));
+  } else {
+    // weight-norm recomposition folded here (HF:343-355)
+    const int taps = c.pos_conv_kernel, Dg = D / c.pos_conv_groups;
     const std::string pc = "encoder.pos_conv_embed.conv.";
     const RawTensor* g = reg.find(pc + "parametrizations.weight.original0");
     const RawTensor* v = reg.find(pc + "parametrizations.weight.original1");
@@ -218,25 +253,7 @@ int svt::encoder_finalize(svt_encoder* e) {
     float* scale;
     SVT_TRY(pool.alloc_t<float>(taps, &scale));
     SVT_TRY(weight_norm_scale(v->dev, g->dev, D, Dg, taps, scale, 0));
-    SVT_TRY(pool.alloc_t<__nv_bfloat16>(static_cast<size_t>(G) * taps * 64 * 64, &e->pos_w));
-    SVT_CUDA(cudaMemset(e->pos_w, 0, sizeof(__nv_bfloat16) * static_cast<size_t>(G) * taps * 64 * 64));
-    // dst[g][j][co][ci] = v[g*Dg+co][ci][j] * scale[j]; for Dg < 64 pack each (co) row block separately
-    if (Dg == 64) {
-      SVT_TRY(pack_posconv_weight(v->dev, scale, D, G, taps, e->pos_w, 0));
-    } else {
-      // generic (base: Dg = 48): build on the host, small one-time cost
-      std::vector<float> hv(v->numel()), hs(taps);
-      SVT_CUDA(cudaMemcpy(hv.data(), v->dev, sizeof(float) * hv.size(), cudaMemcpyDeviceToHost));
-      SVT_CUDA(cudaMemcpy(hs.data(), scale, sizeof(float) * taps, cudaMemcpyDeviceToHost));
-      std::vector<__nv_bfloat16> hp(static_cast<size_t>(G) * taps * 64 * 64, __float2bfloat16(0.f));
-      for (int gi = 0; gi < G; ++gi)
-        for (int j = 0; j < taps; ++j)
-          for (int co = 0; co < Dg; ++co)
-            for (int ci = 0; ci < Dg; ++ci)
-              hp[((static_cast<size_t>(gi) * taps + j) * 64 + co) * 64 + ci] =
-                  __float2bfloat16(hv[(static_cast<size_t>(gi * Dg + co) * Dg + ci) * taps + j] * hs[j]);
-      SVT_CUDA(cudaMemcpy(e->pos_w, hp.data(), sizeof(__nv_bfloat16) * hp.size(), cudaMemcpyHostToDevice));
-    }
+    SVT_TRY(pack_pos(v, scale, &e->pos_w));
     SVT_TRY(pack_vec(pool, reg, pc + "bias", D, 1.f, &e->pos_b));
   }
   SVT_TRY(pack_norm(pool, reg, "encoder.layer_norm.", D, &e->enc_norm));
@@ -371,19 +388,42 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
   __nv_bfloat16* mid = tb.mid;
   float* pre = tb.pre;
   const bool want_stats = stats_out != nullptr;
-  // ---- positional conv embedding + residual: h += GELU(conv(h) + b)
-  {
+  auto pos_conv = [&](const __nv_bfloat16* a, const __nv_bfloat16* w, const float* bias) {
     GemmArgs g;
     g.mode = 1;
-    g.a = hb;
+    g.a = a;
     g.a_dims[0] = D; g.a_dims[1] = T; g.a_dims[2] = B;
     g.a_strides[0] = D; g.a_strides[1] = static_cast<uint64_t>(Ta) * D;
-    g.w = e->pos_w; g.w_rows = c.pos_conv_groups * c.pos_conv_kernel * 64; g.w_cols = 64;
+    g.w = w; g.w_rows = c.pos_conv_groups * c.pos_conv_kernel * 64; g.w_cols = 64;
     g.N = D; g.K = c.pos_conv_kernel * 64;
     g.n_clips = B; g.clip_rows = Ta; g.clip_valid = T; g.pad_left = c.pos_conv_kernel / 2; g.taps = c.pos_conv_kernel;
     g.group_size = D / c.pos_conv_groups;
-    g.bias = e->pos_b; g.resid = h; g.out_f32 = h; g.ld_out = D; g.act = kActGelu;
+    g.bias = bias; g.ld_out = D;
+    return g;
+  };
+  if (c.pos_conv_layers == 0) {
+    // ---- positional conv embedding + residual: h += GELU(conv(h) + b)
+    GemmArgs g = pos_conv(hb, e->pos_w, e->pos_b);
+    g.resid = h; g.out_f32 = h; g.act = kActGelu;
     SVT_TRY(gemm_bf16_tc(g, s));
+  } else {
+    // ---- data2vec-audio: p <- GELU(LN(conv(p) + b)) pos_conv_layers times starting from h, then h += p.
+    // conv output in fp32 (pre), the normalised rows ping-pong through two free bf16 buffers (ctx, qkv)
+    SVT_CUDA(cudaMemsetAsync(pre, 0, static_cast<size_t>(M) * D * 4, s));  // rows t >= T stay zero
+    const __nv_bfloat16* a = hb;
+    for (int i = 0; i < c.pos_conv_layers; ++i) {
+      const bool last = i == c.pos_conv_layers - 1;
+      GemmArgs g = pos_conv(a, e->pos_stack[i].w, e->pos_stack[i].b);
+      g.out_f32 = pre; g.act = kActNone;
+      SVT_TRY(gemm_bf16_tc(g, s));
+      __nv_bfloat16* nxt = (i & 1) ? qkv : ctx;
+      LayerNormArgs ln;
+      ln.x_f32 = pre; ln.gamma = e->ones; ln.beta = e->zeros; ln.rows = M; ln.D = D; ln.eps = 1e-5f; ln.gelu = 1;
+      ln.y_bf16 = last ? nullptr : nxt; ln.y_f32 = last ? pre : nullptr;
+      SVT_TRY(layer_norm(ln, s));
+      a = nxt;
+    }
+    SVT_TRY(add_f32(h, pre, h, static_cast<size_t>(M) * D, s));
   }
   SVT_CUDA(cudaMemsetAsync(ctx, 0, static_cast<size_t>(M) * D * 2, s));  // rows t >= T are never written by attention
 
@@ -529,10 +569,12 @@ static int forward_impl(svt_encoder* e, const float* wav, int B, int L, void* ws
 
   // ---- feature projection: LN(512) -> Linear(512 -> D); fp32 residual stream + bf16 copy for the pos-conv
   {
-    LayerNormArgs ln;
-    ln.x_bf16 = cur; ln.y_bf16 = cur; ln.gamma = e->proj_norm.g; ln.beta = e->proj_norm.b;
-    ln.rows = M; ln.D = C; ln.eps = eps;
-    SVT_TRY(layer_norm(ln, s));
+    if (c.feat_proj_norm) {
+      LayerNormArgs ln;
+      ln.x_bf16 = cur; ln.y_bf16 = cur; ln.gamma = e->proj_norm.g; ln.beta = e->proj_norm.b;
+      ln.rows = M; ln.D = C; ln.eps = eps;
+      SVT_TRY(layer_norm(ln, s));
+    }
     SVT_TRY(linear(cur, M, e->proj, nullptr, h, hb, kActNone, s));
   }
   // ---- positional conv + transformer layers (shared with the video stream)
@@ -568,6 +610,7 @@ int svt_encoder_create(const svt_encoder_config* cfg, svt_encoder** out) {
   if (dh != 64 && dh != 128) return fail(kUnsupported, "head dim must be 64 or 128");
   if (c.ffn_size % 64 != 0) return fail(kUnsupported, "ffn_size must be a multiple of 64");
   if (c.pos_conv_groups <= 0 || c.hidden_size % c.pos_conv_groups != 0) return fail(kInvalidArgument, "bad pos_conv_groups");
+  if (c.pos_conv_kernel <= 0 || c.pos_conv_layers < 0 || c.pos_conv_layers > 16) return fail(kInvalidArgument, "bad positional conv kernel / depth");
   const int dg = c.hidden_size / c.pos_conv_groups;
   if (dg > 64 || dg % 16 != 0) return fail(kUnsupported, "positional conv channels per group must be a multiple of 16, <= 64");
   for (int i = 0; i < c.num_conv_layers; ++i)

@@ -103,6 +103,10 @@ struct svt_encoder {
   svt::LinearW proj;
   __nv_bfloat16* pos_w = nullptr;  // [G][taps][64][64]
   float* pos_b = nullptr;
+  struct PosLayer { __nv_bfloat16* w = nullptr; float* b = nullptr; };
+  std::vector<PosLayer> pos_stack;  // data2vec-audio: cfg.pos_conv_layers x (conv weights as pos_w, bias)
+  float* ones = nullptr;            // [D] affine of the stack's parameter-free LayerNorms
+  float* zeros = nullptr;
   svt::NormW enc_norm;
   struct Layer {
     svt::NormW ln1, ln2;

@@ -32,13 +32,19 @@ def encoder_config_from_hf(cfg, normalize_wav: bool, output_norm: bool) -> Encod
         raise ValueError(f"feat_extract_norm={cfg.feat_extract_norm!r}")
     c.feat_norm_layer = int(cfg.feat_extract_norm == "layer")
     c.stable_layer_norm = int(bool(cfg.do_stable_layer_norm))
-    c.pos_conv_kernel = cfg.num_conv_pos_embeddings
+    if type(cfg).__name__.startswith("Data2Vec"):  # stack of num_conv_pos_embeddings convs of conv_pos_kernel_size taps
+        c.pos_conv_kernel = cfg.conv_pos_kernel_size
+        c.pos_conv_layers = cfg.num_conv_pos_embeddings
+    else:
+        c.pos_conv_kernel = cfg.num_conv_pos_embeddings
+        c.pos_conv_layers = 0
     c.pos_conv_groups = cfg.num_conv_pos_embedding_groups
     c.layer_norm_eps = float(cfg.layer_norm_eps)
     if getattr(cfg, "feat_extract_activation", "gelu") != "gelu" or getattr(cfg, "hidden_act", "gelu") != "gelu":
         raise NotImplementedError("only the exact-erf GELU activation of wav2vec2/HuBERT is built")
     c.normalize_wav = int(bool(normalize_wav))
     c.output_norm = int(bool(output_norm))
+    c.feat_proj_norm = int(bool(getattr(cfg, "feat_proj_layer_norm", True)))  # HubertConfig only; wav2vec2 always has it
     return c
 
 

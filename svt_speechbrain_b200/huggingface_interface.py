@@ -25,12 +25,14 @@ from torch import nn
 from .engine import EncoderEngine, encoder_config_from_hf
 
 try:  # the reference raises the same way (huggingface_interface.py:25-38)
-    from transformers import HubertConfig, HubertModel, Wav2Vec2Config, Wav2Vec2FeatureExtractor, Wav2Vec2Model
+    from transformers import (Data2VecAudioConfig, Data2VecAudioModel, HubertConfig, HubertModel, Wav2Vec2Config,
+                              Wav2Vec2FeatureExtractor, Wav2Vec2Model)
 except ImportError as e:  # pragma: no cover
     raise ImportError("Please install transformers to use the wav2vec2 / HuBERT lobes") from e
 
 # families whose forward is exactly the wav2vec2 graph built in csrc/ (reference table :42-44)
-_FAMILIES = {"wav2vec2": (Wav2Vec2Config, Wav2Vec2Model), "hubert": (HubertConfig, HubertModel)}
+_FAMILIES = {"wav2vec2": (Wav2Vec2Config, Wav2Vec2Model), "hubert": (HubertConfig, HubertModel),
+             "data2vec": (Data2VecAudioConfig, Data2VecAudioModel)}
 
 
 class HuggingFaceWav2Vec2(nn.Module):
@@ -48,7 +50,7 @@ class HuggingFaceWav2Vec2(nn.Module):
             # the reference falls through to an UnboundLocalError here; keep "unknown source" loud but clearer
             raise UnboundLocalError(f"cannot pick a model family from source={source!r} (expected 'wav2vec2' or 'hubert')")
         if family not in _FAMILIES:
-            raise NotImplementedError(f"{family}: not built yet in svt_speechbrain_b200 (wav2vec2 and HuBERT are)")
+            raise NotImplementedError(f"{family}: not built yet in svt_speechbrain_b200 (wav2vec2, HuBERT and data2vec-audio are)")
         config_cls, model_cls = _FAMILIES[family]
         config = config_cls.from_pretrained(source, cache_dir=save_path)
         if family == "hubert" and getattr(config, "conv_pos_batch_norm", False):

@@ -21,7 +21,7 @@ def _build(cfg, seed_sd=None):
     """Reference-shaped modules with the seeded weights of the golden fixtures."""
     import tempfile
 
-    from transformers import Wav2Vec2Config, Wav2Vec2FeatureExtractor, Wav2Vec2Model
+    from transformers import Data2VecAudioConfig, HubertConfig, Wav2Vec2Config, Wav2Vec2FeatureExtractor
 
     import svt_speechbrain_b200 as svt
     from oracle import make_golden as mg
@@ -29,9 +29,10 @@ def _build(cfg, seed_sd=None):
 
     sd = mg.perturb_norm_affines(wo.random_weights(cfg, seed=0), seed=7) if seed_sd is None else seed_sd
     head = wo.random_head(cfg.hidden_size, 20, seed=0)
-    d = os.path.join(tempfile.mkdtemp(), "wav2vec2-test")
+    d = os.path.join(tempfile.mkdtemp(), cfg.family + "-test")  # the lobe picks the family by substring of the path
     os.makedirs(d)
-    Wav2Vec2Config(**cfg.hf_kwargs()).save_pretrained(d)
+    {"hubert": HubertConfig, "data2vec": Data2VecAudioConfig, "wav2vec2": Wav2Vec2Config}[cfg.family](
+        **cfg.hf_kwargs()).save_pretrained(d)
     Wav2Vec2FeatureExtractor(feature_size=1, sampling_rate=16000, padding_value=0.0, do_normalize=True,
                              return_attention_mask=True).save_pretrained(d)
     lobe = svt.HuggingFaceWav2Vec2(source=d, save_path=d, pretrain=False, output_norm=True, freeze=True)
@@ -50,14 +51,16 @@ def _check_logits(got, ref, tag):
     assert rel <= LOGIT_REL_L2 and err <= LOGIT_MAX_ABS, (tag, err, rel)
 
 
-@pytest.mark.parametrize("name", ["w2v2_large_1s", "w2v2_base_1s", "w2v2_large_5s"])
+@pytest.mark.parametrize("name", ["w2v2_large_1s", "w2v2_base_1s", "w2v2_large_5s", "hubert_base_1s", "hubert_large_1s",
+                                  "data2vec_base_1s"])
 def test_encoder_vs_reference_golden(name):
     from oracle import make_golden as mg
     from oracle import wav2vec2_oracle as wo
     import svt_speechbrain_b200 as svt
 
     g = np.load(os.path.join(GOLD, name + ".npz"))
-    cfg = wo.W2V2Config.base() if "base" in name else wo.W2V2Config.large()
+    cfg = {"w2v2_base": wo.W2V2Config.base, "w2v2_large": wo.W2V2Config.large, "hubert_base": wo.W2V2Config.hubert_base,
+           "hubert_large": wo.W2V2Config.hubert_large, "data2vec_base": wo.W2V2Config.data2vec_base}[name.rsplit("_", 1)[0]]()
     lobe, lin, sd, head = _build(cfg)
     wav = mg.synth_wav(int(g["B"]), int(g["L"]), seed=int(g["wav_seed"])).cuda()
     # (1) module-by-module, exactly like AMT.compute_forward: feats = lobe(wav); logits = head(feats)

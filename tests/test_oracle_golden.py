@@ -30,7 +30,10 @@ def test_tiny_stored_weights(name, cfg):
     np.testing.assert_allclose(feats[:, :, :8].numpy(), g["feats_head"], atol=2e-5, rtol=1e-5)
 
 
-@pytest.mark.parametrize("name,cfg", [("w2v2_large_1s", wo.W2V2Config.large()), ("w2v2_base_1s", wo.W2V2Config.base())])
+@pytest.mark.parametrize("name,cfg", [("w2v2_large_1s", wo.W2V2Config.large()), ("w2v2_base_1s", wo.W2V2Config.base()),
+                                      ("hubert_base_1s", wo.W2V2Config.hubert_base()),
+                                      ("hubert_large_1s", wo.W2V2Config.hubert_large()),
+                                      ("data2vec_base_1s", wo.W2V2Config.data2vec_base())])
 def test_full_arch_seeded_weights(name, cfg):
     g = _load(name)
     sd = mg.perturb_norm_affines(wo.random_weights(cfg, seed=int(g["weight_seed"])), seed=int(g["affine_seed"]))

@@ -169,6 +169,12 @@ size_t svt_video_workspace_bytes(const svt_video* v, int batch, int n_frames);
 int svt_video_forward(svt_video* v, const float* video_dev, int batch, int n_frames, void* workspace_dev, size_t workspace_bytes,
                       float* feats_dev, void* stream);
 
+/* Evaluation transform of the video recipe (video_only/train_video_ssl.py:454-457, utils.py:45-84) on the device:
+ * uint8 grey frames (n_frames, height, width) -> x / 255 -> CenterCrop(crop) -> (x - mean) / stdev, fp32
+ * (n_frames, crop, crop) = the (B, 1, T, 88, 88) input of svt_video_forward (crop 88, mean 0.421, stdev 0.165). */
+int svt_video_transform_u8(const uint8_t* frames_dev, long long n_frames, int height, int width, int crop, float mean,
+                           float stdev, float* out_dev, void* stream);
+
 /* ------------------------------------------------------------------ frame post-processing + note decoding */
 /* logits_dev (n_frames, n_out) fp32 device -> octave / pitch-class argmax (first maximum wins, torch
  * semantics) into int32 device arrays.  Columns [oct_off, oct_off+n_oct) and [pc_off, pc_off+n_pc). */

@@ -15,6 +15,7 @@ from .fusion import FusionRCA  # noqa: F401
 from .huggingface_interface import HuggingFaceWav2Vec2  # noqa: F401
 from .linear import Linear  # noqa: F401
 from .utils import decode_arrays, frame2note  # noqa: F401
+from . import feature_cache  # noqa: F401,E402
 
 __all__ = ["HuggingFaceWav2Vec2", "FairseqAVHubertPretrain", "AVTranscriber", "Linear", "FusionRCA", "frame2note", "decode_arrays", "AMTTranscriber", "AMTHparams",
            "split_song", "lib", "SvtError", "LIB_PATH"]

@@ -75,6 +75,7 @@ _SIGS = {
                                  C.POINTER(C.c_int)]),
     "svt_op_gemm": (C.c_int, [_P, C.c_longlong, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                               C.c_int, _P]),
+    "svt_video_transform_u8": (C.c_int, [_P, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P, _P]),
     "svt_op_gemm_ln": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "svt_op_row_stats_cast": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "svt_op_posconv": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

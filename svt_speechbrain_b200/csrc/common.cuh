@@ -202,26 +202,27 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-// Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)), written as relu(x) - 0.5 |x| erfc(|x| / sqrt 2) with
-// erfc(z) = (1 + a1 z + ... + a6 z^6)^-16  (Abramowitz-Stegun 7.1.28, |erf error| <= 3e-7; the 1/sqrt 2 is folded
-// into the coefficients): 6 FFMA + ONE MUFU (rcp) + 4 squarings + 3, abs error < 8e-7 over the whole real line
-// (torch's own fp32 GELU is ~1e-6 from the exact value) -- tests/test_gpu_ops.py::test_gelu_accuracy.
-// One MUFU instead of libm erff's or 7.1.26's two matters: the GEMM epilogues that apply it are MUFU-bound.
+// Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)), written as relu(x) - |x| * (0.5 erfc(|x| / sqrt 2)) with
+// erfc(z) = (1 + a1 z + ... + a6 z^6)^-16  (Abramowitz-Stegun 7.1.28, |erf error| <= 3e-7).  Both the 1 / sqrt 2 and
+// the factor 0.5 (as 2^(1/16) on every coefficient) are folded into the polynomial: 6 FFMA + ONE MUFU (rcp) +
+// 4 squarings + FMNMX + FFMA, abs error < 1e-6 over the whole real line (torch's own fp32 GELU is ~1e-6 from the
+// exact value) -- tests/test_gpu_ops.py::test_gelu_accuracy.  One MUFU instead of libm erff's or 7.1.26's two, and no
+// packed f32x2 form (FFMA2 holds the pipe two cycles on sm_100a, profiles/r1_gelu_microbench.txt).
 __device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x);
-  float p = fmaf(5.38297490493278e-06f, ax, 4.889063711743802e-05f);
-  p = fmaf(p, ax, 3.8003574445610866e-05f);
-  p = fmaf(p, ax, 0.0032776263542473316f);
-  p = fmaf(p, ax, 0.02114100567996502f);
-  p = fmaf(p, ax, 0.04986734688282013f);
-  p = fmaf(p, ax, 1.0f);
+  float p = fmaf(5.62129980608006e-06f, ax, 5.105520904180594e-05f);
+  p = fmaf(p, ax, 3.9686136005911976e-05f);
+  p = fmaf(p, ax, 0.003422739217057824f);
+  p = fmaf(p, ax, 0.02207699790596962f);
+  p = fmaf(p, ax, 0.052075162529945374f);
+  p = fmaf(p, ax, 1.0442737340927124f);
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
   r *= r;
   r *= r;
   r *= r;
-  r *= r;
-  return fmaf(-0.5f * ax, r, fmaxf(x, 0.0f));
+  r *= r;  // = 0.5 erfc(|x| / sqrt 2)
+  return fmaf(-ax, r, fmaxf(x, 0.0f));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -100,6 +100,21 @@ __global__ void __launch_bounds__(256) frontend_im2col_kernel(const float* __res
   }
 }
 
+// Evaluation transform of the video recipe (video_only/train_video_ssl.py:454-457, utils.py:45-84): uint8 frames
+// (n, H, W) -> /255 -> centre crop -> (x - mean) / std, fp32 (n, crop, crop)
+__global__ void __launch_bounds__(256) video_transform_kernel(const uint8_t* __restrict__ frames, long long n, int H, int W,
+                                                              int crop, int y0, int x0, float mean, float stdev,
+                                                              float* __restrict__ out) {
+  const long long total = n * crop * crop;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % crop), y = static_cast<int>((i / crop) % crop);
+    const long long f = i / (static_cast<long long>(crop) * crop);
+    const float v = static_cast<float>(frames[(f * H + y0 + y) * W + x0 + x]);
+    out[i] = (v / 255.0f - mean) / stdev;
+  }
+}
+
 // MaxPool3d((1,3,3), stride (1,2,2), pad (0,1,1)): [N][44][44][64] -> padded [N][24][24][64] (ring = 0)
 __global__ void __launch_bounds__(256) maxpool_kernel(const __nv_bfloat16* __restrict__ f0, int N, __nv_bfloat16* __restrict__ out) {
   constexpr int kR0 = 22, Hp = kR0 + 2, C8 = 64 / 8;
@@ -550,6 +565,21 @@ int svt_video_finalize(svt_video* v) {
 size_t svt_video_workspace_bytes(const svt_video* v, int batch, int n_frames) {
   if (v == nullptr || batch <= 0 || n_frames <= 0) return 0;
   return make_plan(v, batch, n_frames).total;
+}
+
+int svt_video_transform_u8(const uint8_t* frames_dev, long long n_frames, int height, int width, int crop, float mean,
+                           float stdev, float* out_dev, void* stream) {
+  if (frames_dev == nullptr || out_dev == nullptr) return fail(kInvalidArgument, "null argument");
+  if (n_frames <= 0 || crop <= 0 || crop > height || crop > width || stdev == 0.f)
+    return fail(kInvalidArgument, "video transform: bad geometry");
+  // CenterCrop of the reference: delta = int(round(w - tw) / 2.)  (utils.py:79-80)
+  const int x0 = (width - crop) / 2, y0 = (height - crop) / 2;
+  const long long total = n_frames * crop * crop;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(num_sms()) * 16));
+  video_transform_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(frames_dev, n_frames, height, width, crop, y0, x0,
+                                                                              mean, stdev, out_dev);
+  SVT_POST_LAUNCH();
+  return kOk;
 }
 
 int svt_video_forward(svt_video* v, const float* video_dev, int batch, int n_frames, void* workspace_dev, size_t workspace_bytes,

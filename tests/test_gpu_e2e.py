@@ -253,3 +253,27 @@ def test_folded_layer_norm_matches_separate_kernels():
     _check_logits(fold, ref, "folded LayerNorm")
     assert float((sep - fold).abs().max()) > 0.0   # the two paths really are different code
     assert float((sep - fold).abs().max()) < 5e-2
+
+
+def test_feature_cache_stage_a_equals_batch_size_one_extraction(tmp_path):
+    """feature_cache.extract_song_features == the reference's stage-A loop (one utterance per call, features
+    concatenated along frames, audio_only/extract_ssl_feats.py:102-107), and survives the .pt round trip."""
+    from oracle import wav2vec2_oracle as wo
+    from svt_speechbrain_b200 import feature_cache as fc
+    from svt_speechbrain_b200.amt import AMTHparams, split_song
+
+    cfg = wo.W2V2Config.large()
+    lobe, lin, sd, head = _build(cfg)
+    hp = AMTHparams(dur_threshold=1.0)
+    wav = torch.randn(16000 * 3 + 5000, generator=torch.Generator().manual_seed(3))
+    feats = fc.extract_song_features(lobe, wav, hp)
+    ref = torch.cat([lobe(wav[a:b].unsqueeze(0).cuda())[0] for a, b in split_song(wav.numel(), hp)]).cpu()
+    assert feats.shape == ref.shape and feats.dtype == torch.float32
+    assert float((feats - ref).abs().max()) < 5e-3   # batched per-clip statistics vs separate calls
+    with torch.no_grad():
+        o = torch.cat([wo.lobe_forward(cfg, sd, wav[a:b].unsqueeze(0))[0] for a, b in split_song(wav.numel(), hp)])
+    rel = float((feats - o).norm() / o.norm())
+    print("stage-A features vs oracle rel-L2", rel)
+    assert rel < 2e-2
+    p = fc.save_song_features(feats, fc.audio_feats_path(str(tmp_path / "song")))
+    assert torch.equal(torch.load(p), feats)

@@ -139,3 +139,23 @@ def test_audio_visual_pipeline_vs_composed_oracle():
     fi = [(p_on[i], p_off[i], int(octv[i]), int(pc[i])) for i in range(len(p_on))]
     want = np.array(f2n_oracle(fi, 0.4, 0.5, 1 / 49.8), dtype=np.float64).reshape(-1, 3)
     assert notes.shape == want.shape and np.array_equal(notes, want)
+
+
+def test_eval_transform_matches_reference_compose():
+    """svt_video_transform_u8 == Compose([Normalize(0, 255), CenterCrop(88), Normalize(0.421, 0.165)]) of the video
+    recipe (video_only/train_video_ssl.py:454-457; numpy float64 arithmetic there, fp32 here)."""
+    import numpy as np
+    from svt_speechbrain_b200 import video_transforms as vt
+
+    rng = np.random.default_rng(0)
+    for (T, H, W) in [(7, 96, 96), (3, 88, 88), (5, 101, 97)]:
+        frames = rng.integers(0, 256, (2, T, H, W), dtype=np.uint8)
+        x = (frames[0].astype(np.float64) - 0.0) / 255.0                     # Normalize(0, 255)
+        dw, dh = int(round((W - 88)) / 2.), int(round((H - 88)) / 2.)        # CenterCrop (utils.py:79-81)
+        x = x[:, dh:dh + 88, dw:dw + 88]
+        x = (x - 0.421) / 0.165                                              # Normalize(mean, std)
+        got = vt.eval_transform(torch.from_numpy(frames).cuda())
+        assert got.shape == (2, 1, T, 88, 88) and got.dtype == torch.float32
+        assert np.abs(got[0, 0].cpu().numpy() - x).max() < 1e-6
+    with pytest.raises(RuntimeError):
+        vt.eval_transform(torch.zeros(2, 96, 96, dtype=torch.uint8))

@@ -82,6 +82,8 @@ typedef struct svt_encoder_config {
   int pos_conv_layers;     /* 0: one weight-normed grouped conv + GELU (wav2vec2, HuBERT).  n > 0: data2vec-audio's stack
                               of n [grouped conv (kernel pos_conv_kernel, plain weights) -> LayerNorm without affine ->
                               GELU] (Data2VecAudioPositionalConvEmbedding; n = 5, kernel 19) */
+  int rel_pos_buckets;     /* 0: none.  > 0: WavLM's gated relative position bias (WavLMConfig.num_buckets = 320) */
+  int rel_pos_max_distance; /* WavLMConfig.max_bucket_distance = 800 */
 } svt_encoder_config;
 
 int svt_encoder_create(const svt_encoder_config* cfg, svt_encoder** out);
@@ -174,6 +176,10 @@ int svt_video_forward(svt_video* v, const float* video_dev, int batch, int n_fra
  * (n_frames, crop, crop) = the (B, 1, T, 88, 88) input of svt_video_forward (crop 88, mean 0.421, stdev 0.165). */
 int svt_video_transform_u8(const uint8_t* frames_dev, long long n_frames, int height, int width, int crop, float mean,
                            float stdev, float* out_dev, void* stream);
+
+/* HOST helper: bucket of a relative position (key index - query index) exactly as WavLMAttention._relative_positions_bucket
+ * computes it (fp32), exported so the CPU tests can pin it against torch. */
+int svt_wavlm_relative_bucket(int relative_position, int num_buckets, int max_distance);
 
 /* ------------------------------------------------------------------ frame post-processing + note decoding */
 /* logits_dev (n_frames, n_out) fp32 device -> octave / pitch-class argmax (first maximum wins, torch

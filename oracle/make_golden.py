@@ -47,6 +47,10 @@ def perturb_norm_affines(sd, seed=7):
     for k, v in sd.items():
         if "layer_norm" in k and k.endswith(".weight"):
             v = v + 0.1 * torch.randn(v.shape, generator=g)
+        elif k.endswith("gru_rel_pos_const"):  # WavLM: ones at init
+            v = v + 0.3 * torch.randn(v.shape, generator=g)
+        elif k.endswith("rel_attn_embed.weight"):  # WavLM: make the position bias comparable to the scores
+            v = v * 3.0
         elif k.endswith(".bias"):
             v = v + 0.05 * torch.randn(v.shape, generator=g)
         out[k] = v
@@ -131,6 +135,14 @@ def gold_hubert(tmp):
     post-LN layers, NO LayerNorm in the feature projection; large = wav2vec2-large's graph."""
     gold_w2v2("hubert_base_1s", W2V2Config.hubert_base(), B=2, L=16000, tmp=tmp, store_weights=False)
     gold_w2v2("hubert_large_1s", W2V2Config.hubert_large(), B=1, L=16000, tmp=tmp, store_weights=False)
+
+
+def gold_wavlm(tmp):
+    """WavLM through the reference lobe (source path contains "wavlm" -> WavLMModel): gated relative position bias."""
+    gold_w2v2("wavlm_base_1s", W2V2Config.wavlm_base(), B=2, L=16000, tmp=tmp, store_weights=False)
+    gold_w2v2("wavlm_large_1s", W2V2Config.wavlm_large(), B=1, L=16000, tmp=tmp, store_weights=False)
+    # 249 frames: relative distances beyond max_exact = 80 reach the logarithmic buckets
+    gold_w2v2("wavlm_base_5s", W2V2Config.wavlm_base(), B=1, L=80000, tmp=tmp, store_weights=False)
 
 
 def gold_data2vec(tmp):
@@ -218,6 +230,7 @@ def main():
         gold_w2v2("w2v2_large_5s", W2V2Config.large(), B=1, L=80000, tmp=tmp, store_weights=False)
         gold_hubert(tmp)
         gold_data2vec(tmp)
+        gold_wavlm(tmp)
     gold_fusion("fusion_tiny", D=64, d_ffn=96, nhead=4, B=2, Ta=13, Tv=15, store_weights=True)
     gold_fusion("fusion_full", D=1024, d_ffn=3072, nhead=8, B=1, Ta=49, Tv=50, store_weights=False)
     gold_fusion("fusion_full_pad", D=1024, d_ffn=3072, nhead=8, B=2, Ta=49, Tv=45, store_weights=False)

@@ -60,6 +60,9 @@ def make_offline_model_dir(path, config_kwargs, seed=0, family="wav2vec2"):
         HubertModel(HubertConfig(**config_kwargs)).save_pretrained(path)
     elif family == "data2vec":
         Data2VecAudioModel(Data2VecAudioConfig(**config_kwargs)).save_pretrained(path)
+    elif family == "wavlm":
+        from transformers import WavLMConfig, WavLMModel
+        WavLMModel(WavLMConfig(**config_kwargs)).save_pretrained(path)
     else:
         Wav2Vec2Model(Wav2Vec2Config(**config_kwargs)).save_pretrained(path)
     Wav2Vec2FeatureExtractor(

@@ -54,6 +54,19 @@ class W2V2Config:
     # data2vec-audio (HF modeling_data2vec_audio.py): the positional embedding is a stack of num_conv_pos_embeddings
     # (5) layers of [grouped conv k = conv_pos_kernel_size (19) -> LayerNorm without affine -> GELU], no weight norm.
     conv_pos_kernel_size: int = 19
+    # WavLM (HF modeling_wavlm.py, WavLMAttention): bucketed relative position bias, gated per query row
+    num_buckets: int = 320
+    max_bucket_distance: int = 800
+
+    @staticmethod
+    def wavlm_base() -> "W2V2Config":
+        return W2V2Config(family="wavlm")
+
+    @staticmethod
+    def wavlm_large() -> "W2V2Config":
+        c = W2V2Config.large()
+        c.family = "wavlm"
+        return c
 
     @staticmethod
     def data2vec_base() -> "W2V2Config":
@@ -102,7 +115,10 @@ class W2V2Config:
             num_conv_pos_embedding_groups=cfg.num_conv_pos_embedding_groups,
             layer_norm_eps=cfg.layer_norm_eps,
             feat_proj_layer_norm=bool(getattr(cfg, "feat_proj_layer_norm", True)),
-            family={"Hub": "hubert", "Dat": "data2vec"}.get(type(cfg).__name__[:3], "wav2vec2"),
+            family={"Hub": "hubert", "Dat": "data2vec", "Wav": "wav2vec2" if type(cfg).__name__.startswith("Wav2") else "wavlm"}.get(
+                type(cfg).__name__[:3], "wav2vec2"),
+            num_buckets=int(getattr(cfg, "num_buckets", 320)),
+            max_bucket_distance=int(getattr(cfg, "max_bucket_distance", 800)),
             conv_pos_kernel_size=int(getattr(cfg, "conv_pos_kernel_size", 19)),
         )
 
@@ -110,6 +126,8 @@ class W2V2Config:
         extra = {"feat_proj_layer_norm": self.feat_proj_layer_norm} if self.family == "hubert" else {}
         if self.family == "data2vec":
             extra = {"conv_pos_kernel_size": self.conv_pos_kernel_size}
+        if self.family == "wavlm":
+            extra = {"num_buckets": self.num_buckets, "max_bucket_distance": self.max_bucket_distance}
         return dict(
             **extra,
             hidden_size=self.hidden_size,
@@ -183,8 +201,38 @@ def feature_encoder(cfg: W2V2Config, sd, x: torch.Tensor, prefix="model.", taps:
     return h
 
 
-def attention(cfg: W2V2Config, sd, x, p):
-    """HF:466-549 with no attention mask (the lobe passes none, huggingface_interface.py:292)."""
+def wavlm_relative_buckets(cfg: W2V2Config, T: int) -> torch.Tensor:
+    """WavLMAttention._relative_positions_bucket on memory - context positions: (T, T) long, entry [i, j] for key j - query i."""
+    rel = torch.arange(T)[None, :] - torch.arange(T)[:, None]
+    nb = cfg.num_buckets // 2
+    buckets = (rel > 0).long() * nb
+    rel = rel.abs()
+    max_exact = nb // 2
+    large = torch.log(rel.float() / max_exact) / math.log(cfg.max_bucket_distance / max_exact) * (nb - max_exact)
+    large = torch.min((max_exact + large).long(), torch.full_like(rel, nb - 1))
+    return buckets + torch.where(rel < max_exact, rel, large)
+
+
+def wavlm_position_bias(cfg: W2V2Config, sd, prefix: str, T: int) -> torch.Tensor:
+    """compute_bias of layer 0 (the only layer with rel_attn_embed), reused by every layer: (H, T, T)."""
+    emb = sd[prefix + "encoder.layers.0.attention.rel_attn_embed.weight"]  # (num_buckets, H)
+    return emb[wavlm_relative_buckets(cfg, T)].permute(2, 0, 1)
+
+
+def wavlm_gate(cfg: W2V2Config, sd, x, p):
+    """gru_rel_pos gate of WavLMAttention.forward: (B, H, T) from the attention input rows x (B, T, D)."""
+    B, T, D = x.shape
+    H = cfg.num_attention_heads
+    xh = x.view(B, T, H, D // H).permute(0, 2, 1, 3)
+    proj = F.linear(xh, sd[p + "gru_rel_pos_linear.weight"], sd[p + "gru_rel_pos_linear.bias"])
+    proj = proj.view(B, H, T, 2, 4).sum(-1)
+    ga, gb = torch.sigmoid(proj).chunk(2, dim=-1)
+    return (ga * (gb * sd[p + "gru_rel_pos_const"] - 1.0) + 2.0).squeeze(-1)
+
+
+def attention(cfg: W2V2Config, sd, x, p, pos_bias: Optional[torch.Tensor] = None):
+    """HF:466-549 with no attention mask (the lobe passes none, huggingface_interface.py:292).  WavLM: the scores get
+    gate[b, h, i] * pos_bias[h, i, j] added before the softmax (additive attn_mask of F.multi_head_attention_forward)."""
     B, T, D = x.shape
     H = cfg.num_attention_heads
     dh = D // H
@@ -195,6 +243,8 @@ def attention(cfg: W2V2Config, sd, x, p):
     k = k.view(B, T, H, dh).transpose(1, 2)
     v = v.view(B, T, H, dh).transpose(1, 2)
     w = torch.matmul(q, k.transpose(2, 3)) * (dh ** -0.5)
+    if pos_bias is not None:
+        w = w + wavlm_gate(cfg, sd, x, p)[:, :, :, None] * pos_bias[None]
     w = torch.softmax(w, dim=-1)
     o = torch.matmul(w, v).transpose(1, 2).reshape(B, T, D)
     return F.linear(o, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
@@ -241,13 +291,14 @@ def encoder(cfg: W2V2Config, sd, h, prefix="model.", taps: Optional[dict] = None
         taps["pos"] = h
     if not cfg.do_stable_layer_norm:
         h = _ln(sd, h, e + "layer_norm.", eps)  # HF:692
+    pb = wavlm_position_bias(cfg, sd, prefix, h.shape[1]) if cfg.family == "wavlm" else None
     for l in range(cfg.num_hidden_layers):
         p = f"{e}layers.{l}."
         if cfg.do_stable_layer_norm:  # HF:612-655
-            h = h + attention(cfg, sd, _ln(sd, h, p + "layer_norm.", eps), p + "attention.")
+            h = h + attention(cfg, sd, _ln(sd, h, p + "layer_norm.", eps), p + "attention.", pb)
             h = h + feed_forward(sd, _ln(sd, h, p + "final_layer_norm.", eps), p + "feed_forward.")
         else:  # HF:576-609
-            h = _ln(sd, h + attention(cfg, sd, h, p + "attention."), p + "layer_norm.", eps)
+            h = _ln(sd, h + attention(cfg, sd, h, p + "attention.", pb), p + "layer_norm.", eps)
             h = _ln(sd, h + feed_forward(sd, h, p + "feed_forward."), p + "final_layer_norm.", eps)
         if taps is not None:
             taps[f"layer{l}"] = h
@@ -320,6 +371,9 @@ def random_weights(cfg: W2V2Config, seed: int = 0) -> Dict[str, torch.Tensor]:
         m = HubertModel(HubertConfig(**cfg.hf_kwargs())).eval()
     elif cfg.family == "data2vec":
         m = Data2VecAudioModel(Data2VecAudioConfig(**cfg.hf_kwargs())).eval()
+    elif cfg.family == "wavlm":
+        from transformers import WavLMConfig, WavLMModel
+        m = WavLMModel(WavLMConfig(**cfg.hf_kwargs())).eval()
     else:
         m = Wav2Vec2Model(Wav2Vec2Config(**cfg.hf_kwargs())).eval()
     return {"model." + k: v.detach().clone().float() for k, v in m.state_dict().items()}

@@ -18,7 +18,7 @@ class EncoderConfig(C.Structure):
         ("conv_bias", C.c_int), ("feat_norm_layer", C.c_int), ("stable_layer_norm", C.c_int),
         ("pos_conv_kernel", C.c_int), ("pos_conv_groups", C.c_int), ("layer_norm_eps", C.c_float),
         ("normalize_wav", C.c_int), ("output_norm", C.c_int), ("feat_proj_norm", C.c_int),
-        ("pos_conv_layers", C.c_int),
+        ("pos_conv_layers", C.c_int), ("rel_pos_buckets", C.c_int), ("rel_pos_max_distance", C.c_int),
     ]
 
 
@@ -75,6 +75,7 @@ _SIGS = {
                                  C.POINTER(C.c_int)]),
     "svt_op_gemm": (C.c_int, [_P, C.c_longlong, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                               C.c_int, _P]),
+    "svt_wavlm_relative_bucket": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "svt_video_transform_u8": (C.c_int, [_P, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P, _P]),
     "svt_op_gemm_ln": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "svt_op_row_stats_cast": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),

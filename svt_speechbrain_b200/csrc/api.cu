@@ -113,6 +113,10 @@ int svt_op_gemm_ln(const void* a_bf16, const void* w_bf16, const float* bias, co
   return gemm_bf16_tc(g, static_cast<cudaStream_t>(stream));
 }
 
+int svt_wavlm_relative_bucket(int relative_position, int num_buckets, int max_distance) {
+  return wavlm_relative_bucket(relative_position, num_buckets, max_distance);
+}
+
 int svt_op_row_stats_cast(const float* x, int rows, int D, void* y_bf16, float* stats, void* stream) {
   if (x == nullptr || y_bf16 == nullptr || stats == nullptr) return fail(kInvalidArgument, "null argument");
   return row_stats_cast(x, rows, D, static_cast<__nv_bfloat16*>(y_bf16), stats, static_cast<cudaStream_t>(stream));

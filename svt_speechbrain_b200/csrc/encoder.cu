@@ -283,6 +283,27 @@ int svt::encoder_finalize(svt_encoder* e) {
     SVT_TRY(pack_linear(pool, reg, p + "attention.out_proj.", D, D, &L.out));
     SVT_TRY(pack_linear(pool, reg, p + "feed_forward.intermediate_dense.", F, D, &L.ff1));
     SVT_TRY(pack_linear(pool, reg, p + "feed_forward.output_dense.", D, F, &L.ff2));
+    if (c.rel_pos_buckets > 0) {
+      // WavLM gate: (Linear(64 -> 8)).view(2, 4).sum(-1) == Linear(64 -> 2) with the 4-row groups of W / b summed
+      const RawTensor *gw, *gb, *gc;
+      SVT_TRY(reg.require(p + "attention.gru_rel_pos_linear.weight", {8, dh}, &gw));
+      SVT_TRY(reg.require(p + "attention.gru_rel_pos_linear.bias", {8}, &gb));
+      gc = reg.find(p + "attention.gru_rel_pos_const");
+      if (gc == nullptr || gc->numel() != static_cast<size_t>(H)) return fail(kUnknownTensor, "missing " + p + "attention.gru_rel_pos_const");
+      std::vector<float> hw(8 * dh), hb8(8), w2(2 * dh, 0.f), b2(2, 0.f);
+      SVT_CUDA(cudaMemcpy(hw.data(), gw->dev, sizeof(float) * hw.size(), cudaMemcpyDeviceToHost));
+      SVT_CUDA(cudaMemcpy(hb8.data(), gb->dev, sizeof(float) * 8, cudaMemcpyDeviceToHost));
+      for (int r = 0; r < 8; ++r) {
+        for (int k = 0; k < dh; ++k) w2[(r / 4) * dh + k] += hw[r * dh + k];
+        b2[r / 4] += hb8[r];
+      }
+      SVT_TRY(pool.alloc_t<float>(w2.size(), &L.gate_w2));
+      SVT_TRY(pool.alloc_t<float>(2, &L.gate_b2));
+      SVT_TRY(pool.alloc_t<float>(H, &L.gate_const));
+      SVT_CUDA(cudaMemcpy(L.gate_w2, w2.data(), sizeof(float) * w2.size(), cudaMemcpyHostToDevice));
+      SVT_CUDA(cudaMemcpy(L.gate_b2, b2.data(), sizeof(float) * 2, cudaMemcpyHostToDevice));
+      SVT_CUDA(cudaMemcpy(L.gate_const, gc->dev, sizeof(float) * H, cudaMemcpyDeviceToDevice));
+    }
     if (transformer_rowstats_bytes(e, 1) > 0) {
       // second copies of the two Linears that read a LayerNorm, with the norm folded in
       L.qkv_ln.N = 3 * D; L.qkv_ln.K = D;
@@ -306,6 +327,14 @@ int svt::encoder_finalize(svt_encoder* e) {
     }
     e->layers.push_back(L);
   }
+  e->rel_tabs.clear();  // device tables belonged to the pool released above
+  e->rel_embed.clear();
+  if (c.rel_pos_buckets > 0) {
+    const RawTensor* emb;
+    SVT_TRY(reg.require("encoder.layers.0.attention.rel_attn_embed.weight", {c.rel_pos_buckets, H}, &emb));
+    e->rel_embed.resize(emb->numel());
+    SVT_CUDA(cudaMemcpy(e->rel_embed.data(), emb->dev, sizeof(float) * emb->numel(), cudaMemcpyDeviceToHost));
+  }
   SVT_CUDA(cudaDeviceSynchronize());
   e->reg.clear();  // fp32 staging copies no longer needed
   e->finalized = true;
@@ -316,7 +345,7 @@ int svt::encoder_finalize(svt_encoder* e) {
 namespace {
 struct EncPlan {
   int B, L, T0a, Tn, Tna, M;  // Tn: valid output frames, Tna: allocated frames per clip, M = B * Tna
-  size_t off_stats, off_chan, off_bufA, off_bufB, off_h, off_hb, off_qkv, off_ctx, off_mid, off_pre, off_rowstats, total;
+  size_t off_stats, off_chan, off_bufA, off_bufB, off_h, off_hb, off_qkv, off_ctx, off_mid, off_pre, off_rowstats, off_gate, total;
 };
 EncPlan make_plan(const svt_encoder* e, int B, int L) {
   const svt_encoder_config& c = e->cfg;
@@ -344,6 +373,7 @@ EncPlan make_plan(const svt_encoder* e, int B, int L) {
   p.off_mid = take(static_cast<size_t>(p.M) * F * 2);
   p.off_pre = take(static_cast<size_t>(p.M) * D * 4);
   p.off_rowstats = take(transformer_rowstats_bytes(e, static_cast<size_t>(p.M)));
+  p.off_gate = take(c.rel_pos_buckets > 0 ? sizeof(float) * static_cast<size_t>(p.M) * c.num_heads : 0);
   p.total = off;
   return p;
 }
@@ -434,17 +464,42 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
     ln.stats_stride = stats_stride;
     return layer_norm(ln, s);
   };
-  auto attend = [&]() {
+  // WavLM: Toeplitz position-bias table of this T (built once per T on the host, cached on the device) and, per
+  // layer, the per-row gates from the attention input rows
+  const float* rel_tab = nullptr;
+  if (c.rel_pos_buckets > 0) {
+    auto it = e->rel_tabs.find(T);
+    if (it == e->rel_tabs.end()) {
+      std::vector<float> tab(static_cast<size_t>(H) * (2 * T - 1));
+      for (int d = -(T - 1); d <= T - 1; ++d) {
+        const int bucket = wavlm_relative_bucket(d, c.rel_pos_buckets, c.rel_pos_max_distance);
+        for (int hh = 0; hh < H; ++hh)
+          tab[static_cast<size_t>(hh) * (2 * T - 1) + d + T - 1] = e->rel_embed[static_cast<size_t>(bucket) * H + hh];
+      }
+      float* dev = nullptr;
+      SVT_TRY(const_cast<svt_encoder*>(e)->pool.alloc_t<float>(tab.size(), &dev));
+      SVT_CUDA(cudaMemcpyAsync(dev, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, s));
+      SVT_CUDA(cudaStreamSynchronize(s));  // `tab` is pageable host memory going out of scope
+      it = e->rel_tabs.emplace(T, dev).first;
+    }
+    rel_tab = it->second;
+  }
+  auto attend = [&](const svt_encoder::Layer& Lw, const __nv_bfloat16* x_rows) {
     AttentionArgs a;
     a.q = qkv; a.k = qkv + D; a.v = qkv + 2 * D; a.o = ctx;
     a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
     a.Tq = T; a.Tk = T; a.q_clip_rows = Ta; a.k_clip_rows = Ta; a.clips = B; a.heads = H; a.head_dim = dh;
+    if (rel_tab != nullptr) {
+      SVT_TRY(wavlm_gate(x_rows, M, H, Lw.gate_w2, Lw.gate_b2, Lw.gate_const, tb.gate, s));
+      a.rel_tab = rel_tab; a.gate = tb.gate;
+    }
     return attention_bf16(a, s);
   };
   if (want_stats) SVT_CUDA(cudaMemsetAsync(stats_out, 0, 2 * sizeof(double) * (stats_stride > 0 ? B : 1), s));
   const float* final_x = nullptr;
 
-  if (c.stable_layer_norm && get_option_ln_fold() != 0 && c.num_layers > 0 && transformer_rowstats_bytes(e, M) > 0) {
+  if (c.stable_layer_norm && get_option_ln_fold() != 0 && c.num_layers > 0 && transformer_rowstats_bytes(e, M) > 0 &&
+      c.rel_pos_buckets == 0) {  // (WavLM's gate needs the normalised rows themselves)
     // pre-LN layers (HF:612-655) with both per-layer LayerNorms folded around the GEMMs: the GEMM that writes the
     // residual stream also writes its bf16 copy and per-row (sum, sum of squares); the GEMM that reads LN(h) runs on
     // the un-normalised copy with gamma folded into W and finishes the normalisation in its epilogue.
@@ -454,7 +509,7 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
     for (int l = 0; l < c.num_layers; ++l) {
       const svt_encoder::Layer& Lw = e->layers[l];
       SVT_TRY(linear(hb, M, Lw.qkv_ln, nullptr, nullptr, qkv, kActNone, s, nullptr, st, eps));
-      SVT_TRY(attend());
+      SVT_TRY(attend(Lw, hb));
       SVT_TRY(linear(ctx, M, Lw.out, h, h, hb, kActNone, s, st_mid));
       SVT_TRY(linear(hb, M, Lw.ff1_ln, nullptr, nullptr, mid, kActGelu, s, nullptr, st_mid, eps));
       SVT_TRY(linear(mid, M, Lw.ff2, h, h, hb, kActNone, s, st));
@@ -467,7 +522,7 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
       const svt_encoder::Layer& Lw = e->layers[l];
       SVT_TRY(ln_rows(h, Lw.ln1, hb, nullptr, nullptr));
       SVT_TRY(linear(hb, M, Lw.qkv, nullptr, nullptr, qkv, kActNone, s));
-      SVT_TRY(attend());
+      SVT_TRY(attend(Lw, hb));
       SVT_TRY(linear(ctx, M, Lw.out, h, h, nullptr, kActNone, s));
       SVT_TRY(ln_rows(h, Lw.ln2, hb, nullptr, nullptr));
       SVT_TRY(linear(hb, M, Lw.ff1, nullptr, nullptr, mid, kActGelu, s));
@@ -483,7 +538,7 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
       const svt_encoder::Layer& Lw = e->layers[l];
       const bool last = l == c.num_layers - 1;
       SVT_TRY(linear(hb, M, Lw.qkv, nullptr, nullptr, qkv, kActNone, s));
-      SVT_TRY(attend());
+      SVT_TRY(attend(Lw, hb));
       SVT_TRY(linear(ctx, M, Lw.out, h, h, nullptr, kActNone, s));
       SVT_TRY(ln_rows(h, Lw.ln1, hb, h, nullptr));
       SVT_TRY(linear(hb, M, Lw.ff1, nullptr, nullptr, mid, kActGelu, s));
@@ -584,6 +639,7 @@ static int forward_impl(svt_encoder* e, const float* wav, int B, int L, void* ws
     TransformerBuffers tb;
     tb.h = h; tb.hb = hb; tb.qkv = qkv; tb.ctx = ctx; tb.mid = mid; tb.pre = pre;
     tb.rowstats = reinterpret_cast<float*>(base + p.off_rowstats);
+    tb.gate = reinterpret_cast<float*>(base + p.off_gate);
     SVT_TRY(encoder_transformer_forward(e, B, T, Ta, tb, want_stats ? stats_out : nullptr, stats_stride, &final_x, s));
   }
   // ---- A7 whole-tensor output norm + head
@@ -611,6 +667,8 @@ int svt_encoder_create(const svt_encoder_config* cfg, svt_encoder** out) {
   if (c.ffn_size % 64 != 0) return fail(kUnsupported, "ffn_size must be a multiple of 64");
   if (c.pos_conv_groups <= 0 || c.hidden_size % c.pos_conv_groups != 0) return fail(kInvalidArgument, "bad pos_conv_groups");
   if (c.pos_conv_kernel <= 0 || c.pos_conv_layers < 0 || c.pos_conv_layers > 16) return fail(kInvalidArgument, "bad positional conv kernel / depth");
+  if (c.rel_pos_buckets < 0 || c.rel_pos_buckets % 4 != 0 || (c.rel_pos_buckets > 0 && (c.rel_pos_max_distance <= c.rel_pos_buckets / 4 || dh != 64)))
+    return fail(kInvalidArgument, "bad relative position bias configuration (needs head dim 64)");
   const int dg = c.hidden_size / c.pos_conv_groups;
   if (dg > 64 || dg % 16 != 0) return fail(kUnsupported, "positional conv channels per group must be a multiple of 16, <= 64");
   for (int i = 0; i < c.num_conv_layers; ++i)

@@ -72,6 +72,7 @@ namespace svt {
 // transformer_rowstats_bytes() (per-row sum / sum of squares links of the folded-LayerNorm chain)
 struct TransformerBuffers {
   float* rowstats = nullptr;
+  float* gate = nullptr;  // WavLM: [M][heads] fp32
   float* h = nullptr;
   __nv_bfloat16* hb = nullptr;
   __nv_bfloat16* qkv = nullptr;
@@ -112,7 +113,13 @@ struct svt_encoder {
     svt::NormW ln1, ln2;
     svt::LinearW qkv, out, ff1, ff2;
     svt::LinearW qkv_ln, ff1_ln;  // pre-LN models: gamma / beta of ln1 / ln2 folded in (option "ln_fold")
+    // WavLM: gru_rel_pos_linear with its 2 x 4 output groups summed ([2][64] + [2]) and gru_rel_pos_const [H]
+    float* gate_w2 = nullptr;
+    float* gate_b2 = nullptr;
+    float* gate_const = nullptr;
   };
+  std::vector<float> rel_embed;                 // WavLM: layers.0.attention.rel_attn_embed.weight [buckets][H] (host)
+  mutable std::map<int, float*> rel_tabs;       // T -> device table [H][2T - 1] of the Toeplitz position bias (pool-owned)
   std::vector<Layer> layers;
   float* head_w = nullptr;  // [n_out, D] fp32
   float* head_b = nullptr;

@@ -14,6 +14,11 @@ struct AttentionArgs {
   int Tq = 0, Tk = 0;                   // valid rows per clip
   int q_clip_rows = 0, k_clip_rows = 0; // allocated rows per clip
   int clips = 0, heads = 0, head_dim = 0;
+  // WavLM gated relative position bias (HF modeling_wavlm.py, WavLMAttention.forward): the score of (query i, key j) gets
+  // gate[(clip * q_clip_rows + i) * heads + head] * rel_tab[head * (2 * Tk - 1) + (j - i) + Tk - 1] added before the
+  // softmax.  Self-attention only (Tq == Tk); served by the mma.sync kernel.
+  const float* rel_tab = nullptr;
+  const float* gate = nullptr;
 };
 int attention_bf16(const AttentionArgs& a, cudaStream_t stream);       // dispatcher
 int attention_bf16_tc(const AttentionArgs& a, cudaStream_t stream);    // tcgen05 / TMEM kernel (attention_tc.cu), head_dim 64
@@ -44,6 +49,12 @@ struct LayerNormArgs {
 int layer_norm(const LayerNormArgs& a, cudaStream_t stream);
 // Folded-LayerNorm helpers (GemmArgs::ln_stats): y = bf16(x) plus per-row (sum, sum of squares) -> stats [rows][2];
 // and the per-feature vectors of a folded weight: colsum[n] = sum_k w_packed[n][k], bias[n] += scale * w_f32[n].beta
+// WavLM: gate[row][head] = ga * (gb * const[head] - 1) + 2 with (ga, gb) = sigmoid(w2 . x_head + b2), x = rows [M, heads*64]
+// bf16, w2 [2][64] / b2 [2] = gru_rel_pos_linear with its 2 x 4 output groups summed (the sums commute with the Linear)
+int wavlm_gate(const __nv_bfloat16* x, int rows, int heads, const float* w2, const float* b2, const float* head_const,
+               float* gate, cudaStream_t stream);
+// bucket of a relative position (key - query) as WavLMAttention._relative_positions_bucket computes it in fp32 (host)
+int wavlm_relative_bucket(int relative_position, int num_buckets, int max_distance);
 int row_stats_cast(const float* x, int rows, int D, __nv_bfloat16* y, float* stats, cudaStream_t stream);
 int ln_fold_vectors(const float* w_f32, const __nv_bfloat16* w_packed, const float* beta, float scale, int N, int K,
                     float* colsum, float* bias, cudaStream_t stream);

@@ -1,6 +1,7 @@
 // HBM-bound row kernels of the hot path: layer norms, the C_in=1 first conv layer (fused with the
 // whole-tensor input normalisation, LayerNorm and GELU), whole-tensor output norm + linear head,
 // frame post-processing.  All use 16-byte vectorised, warp-coalesced accesses and warp-shuffle reductions.
+#include <cmath>
 #include "ops.cuh"
 
 namespace svt {
@@ -430,6 +431,40 @@ __global__ void ln_fold_vectors_kernel(const float* __restrict__ w_f32, const __
   }
 }
 
+// WavLM gate: one warp per row, lane pair (2h, 2h + 1) owns head h (64 channels)
+__global__ void __launch_bounds__(256) wavlm_gate_kernel(const __nv_bfloat16* __restrict__ x, int rows, int heads,
+                                                         const float* __restrict__ w2, const float* __restrict__ b2,
+                                                         const float* __restrict__ head_const, float* __restrict__ gate) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int D = heads * 64;
+  for (int base = 0; base < D; base += 1024) {  // 32 lanes x 32 channels per pass
+    const int c0 = base + lane * 32;
+    float a = 0.f, b = 0.f;
+    if (c0 < D) {
+      const __nv_bfloat16* xr = x + static_cast<size_t>(row) * D + c0;
+      const int w0 = (lane & 1) * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 v = ld_bf16x4(xr + i);
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(w2 + w0 + i));
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(w2 + 64 + w0 + i));
+        a += v.x * wa.x + v.y * wa.y + v.z * wa.z + v.w * wa.w;
+        b += v.x * wb.x + v.y * wb.y + v.z * wb.z + v.w * wb.w;
+      }
+    }
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    b += __shfl_xor_sync(0xffffffffu, b, 1);
+    if (c0 < D && (lane & 1) == 0) {
+      const int h = c0 >> 6;
+      const float ga = 1.f / (1.f + __expf(-(a + b2[0])));
+      const float gb = 1.f / (1.f + __expf(-(b + b2[1])));
+      gate[static_cast<size_t>(row) * heads + h] = ga * (gb * head_const[h] - 1.f) + 2.f;
+    }
+  }
+}
+
 template <typename F>
 int dispatch_nv(int D, F&& f) {
   switch (D / 128) {
@@ -457,6 +492,29 @@ int layer_norm(const LayerNormArgs& a, cudaStream_t stream) {
     SVT_POST_LAUNCH();
     return static_cast<int>(kOk);
   });
+}
+
+int wavlm_gate(const __nv_bfloat16* x, int rows, int heads, const float* w2, const float* b2, const float* head_const,
+               float* gate, cudaStream_t stream) {
+  if (rows <= 0) return kOk;
+  wavlm_gate_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(x, rows, heads, w2, b2, head_const, gate);
+  SVT_POST_LAUNCH();
+  return kOk;
+}
+
+int wavlm_relative_bucket(int relative_position, int num_buckets, int max_distance) {
+  // fp32 arithmetic in the order torch evaluates WavLMAttention._relative_positions_bucket
+  const int nb = num_buckets / 2;
+  int bucket = relative_position > 0 ? nb : 0;
+  const int rel = relative_position < 0 ? -relative_position : relative_position;
+  const int max_exact = nb / 2;
+  if (rel < max_exact) return bucket + rel;
+  float v = std::log(static_cast<float>(rel) / static_cast<float>(max_exact));
+  v = v / static_cast<float>(std::log(static_cast<double>(max_distance) / max_exact));
+  v = v * static_cast<float>(nb - max_exact);
+  long large = static_cast<long>(static_cast<float>(max_exact) + v);
+  if (large > nb - 1) large = nb - 1;
+  return bucket + static_cast<int>(large);
 }
 
 int row_stats_cast(const float* x, int rows, int D, __nv_bfloat16* y, float* stats, cudaStream_t stream) {

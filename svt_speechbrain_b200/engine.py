@@ -44,6 +44,9 @@ def encoder_config_from_hf(cfg, normalize_wav: bool, output_norm: bool) -> Encod
         raise NotImplementedError("only the exact-erf GELU activation of wav2vec2/HuBERT is built")
     c.normalize_wav = int(bool(normalize_wav))
     c.output_norm = int(bool(output_norm))
+    if type(cfg).__name__.startswith("WavLM"):
+        c.rel_pos_buckets = cfg.num_buckets
+        c.rel_pos_max_distance = cfg.max_bucket_distance
     c.feat_proj_norm = int(bool(getattr(cfg, "feat_proj_layer_norm", True)))  # HubertConfig only; wav2vec2 always has it
     return c
 

@@ -26,13 +26,13 @@ from .engine import EncoderEngine, encoder_config_from_hf
 
 try:  # the reference raises the same way (huggingface_interface.py:25-38)
     from transformers import (Data2VecAudioConfig, Data2VecAudioModel, HubertConfig, HubertModel, Wav2Vec2Config,
-                              Wav2Vec2FeatureExtractor, Wav2Vec2Model)
+                              Wav2Vec2FeatureExtractor, Wav2Vec2Model, WavLMConfig, WavLMModel)
 except ImportError as e:  # pragma: no cover
     raise ImportError("Please install transformers to use the wav2vec2 / HuBERT lobes") from e
 
 # families whose forward is exactly the wav2vec2 graph built in csrc/ (reference table :42-44)
 _FAMILIES = {"wav2vec2": (Wav2Vec2Config, Wav2Vec2Model), "hubert": (HubertConfig, HubertModel),
-             "data2vec": (Data2VecAudioConfig, Data2VecAudioModel)}
+             "data2vec": (Data2VecAudioConfig, Data2VecAudioModel), "wavlm": (WavLMConfig, WavLMModel)}
 
 
 class HuggingFaceWav2Vec2(nn.Module):

@@ -27,8 +27,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_config_struct_layout_matches_header():
-    # 6 ints + 2 * 8 ints + 5 ints + float + 4 ints
-    assert C.sizeof(_lib.EncoderConfig) == 4 * (6 + 16 + 5 + 1 + 4)
+    # 6 ints + 2 * 8 ints + 5 ints + float + 6 ints
+    assert C.sizeof(_lib.EncoderConfig) == 4 * (6 + 16 + 5 + 1 + 6)
     assert C.sizeof(_lib.FusionConfig) == 16
 
 
@@ -107,3 +107,17 @@ def test_shard_ranges_cover_everything():
         for w in (1, 2, 4, 8):
             r = [shard_range(n, k, w) for k in range(w)]
             assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+
+
+def test_wavlm_relative_bucket_matches_torch():
+    """svt_wavlm_relative_bucket (host, fp32) == WavLMAttention._relative_positions_bucket as the oracle restates it
+    (pinned to the reference by the wavlm_* goldens), for every relative position a 60-s clip can produce."""
+    import torch  # noqa: F401
+    from oracle import wav2vec2_oracle as wo
+    cfg = wo.W2V2Config.wavlm_base()
+    T = 3000
+    b = wo.wavlm_relative_buckets(cfg, T)
+    L = _lib.lib()
+    for d in range(T):
+        assert L.svt_wavlm_relative_bucket(d, cfg.num_buckets, cfg.max_bucket_distance) == int(b[0, d])
+        assert L.svt_wavlm_relative_bucket(-d, cfg.num_buckets, cfg.max_bucket_distance) == int(b[d, 0])

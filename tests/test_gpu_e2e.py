@@ -21,7 +21,7 @@ def _build(cfg, seed_sd=None):
     """Reference-shaped modules with the seeded weights of the golden fixtures."""
     import tempfile
 
-    from transformers import Data2VecAudioConfig, HubertConfig, Wav2Vec2Config, Wav2Vec2FeatureExtractor
+    from transformers import Data2VecAudioConfig, HubertConfig, Wav2Vec2Config, Wav2Vec2FeatureExtractor, WavLMConfig
 
     import svt_speechbrain_b200 as svt
     from oracle import make_golden as mg
@@ -31,7 +31,7 @@ def _build(cfg, seed_sd=None):
     head = wo.random_head(cfg.hidden_size, 20, seed=0)
     d = os.path.join(tempfile.mkdtemp(), cfg.family + "-test")  # the lobe picks the family by substring of the path
     os.makedirs(d)
-    {"hubert": HubertConfig, "data2vec": Data2VecAudioConfig, "wav2vec2": Wav2Vec2Config}[cfg.family](
+    {"hubert": HubertConfig, "data2vec": Data2VecAudioConfig, "wav2vec2": Wav2Vec2Config, "wavlm": WavLMConfig}[cfg.family](
         **cfg.hf_kwargs()).save_pretrained(d)
     Wav2Vec2FeatureExtractor(feature_size=1, sampling_rate=16000, padding_value=0.0, do_normalize=True,
                              return_attention_mask=True).save_pretrained(d)
@@ -52,7 +52,7 @@ def _check_logits(got, ref, tag):
 
 
 @pytest.mark.parametrize("name", ["w2v2_large_1s", "w2v2_base_1s", "w2v2_large_5s", "hubert_base_1s", "hubert_large_1s",
-                                  "data2vec_base_1s"])
+                                  "data2vec_base_1s", "wavlm_base_1s", "wavlm_large_1s", "wavlm_base_5s"])
 def test_encoder_vs_reference_golden(name):
     from oracle import make_golden as mg
     from oracle import wav2vec2_oracle as wo
@@ -60,7 +60,8 @@ def test_encoder_vs_reference_golden(name):
 
     g = np.load(os.path.join(GOLD, name + ".npz"))
     cfg = {"w2v2_base": wo.W2V2Config.base, "w2v2_large": wo.W2V2Config.large, "hubert_base": wo.W2V2Config.hubert_base,
-           "hubert_large": wo.W2V2Config.hubert_large, "data2vec_base": wo.W2V2Config.data2vec_base}[name.rsplit("_", 1)[0]]()
+           "hubert_large": wo.W2V2Config.hubert_large, "data2vec_base": wo.W2V2Config.data2vec_base,
+           "wavlm_base": wo.W2V2Config.wavlm_base, "wavlm_large": wo.W2V2Config.wavlm_large}[name.rsplit("_", 1)[0]]()
     lobe, lin, sd, head = _build(cfg)
     wav = mg.synth_wav(int(g["B"]), int(g["L"]), seed=int(g["wav_seed"])).cuda()
     # (1) module-by-module, exactly like AMT.compute_forward: feats = lobe(wav); logits = head(feats)

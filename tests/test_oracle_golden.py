@@ -33,7 +33,10 @@ def test_tiny_stored_weights(name, cfg):
 @pytest.mark.parametrize("name,cfg", [("w2v2_large_1s", wo.W2V2Config.large()), ("w2v2_base_1s", wo.W2V2Config.base()),
                                       ("hubert_base_1s", wo.W2V2Config.hubert_base()),
                                       ("hubert_large_1s", wo.W2V2Config.hubert_large()),
-                                      ("data2vec_base_1s", wo.W2V2Config.data2vec_base())])
+                                      ("data2vec_base_1s", wo.W2V2Config.data2vec_base()),
+                                      ("wavlm_base_1s", wo.W2V2Config.wavlm_base()),
+                                      ("wavlm_large_1s", wo.W2V2Config.wavlm_large()),
+                                      ("wavlm_base_5s", wo.W2V2Config.wavlm_base())])
 def test_full_arch_seeded_weights(name, cfg):
     g = _load(name)
     sd = mg.perturb_norm_affines(wo.random_weights(cfg, seed=int(g["weight_seed"])), seed=int(g["affine_seed"]))

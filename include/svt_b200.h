@@ -84,6 +84,8 @@ typedef struct svt_encoder_config {
                               GELU] (Data2VecAudioPositionalConvEmbedding; n = 5, kernel 19) */
   int rel_pos_buckets;     /* 0: none.  > 0: WavLM's gated relative position bias (WavLMConfig.num_buckets = 320) */
   int rel_pos_max_distance; /* WavLMConfig.max_bucket_distance = 800 */
+  int pos_conv_batch_norm; /* HubertConfig.conv_pos_batch_norm: eval-mode BatchNorm1d before a plain (not weight-normed)
+                              positional conv (HF modeling_hubert.py, HubertPositionalConvEmbedding) */
 } svt_encoder_config;
 
 int svt_encoder_create(const svt_encoder_config* cfg, svt_encoder** out);

@@ -47,6 +47,12 @@ def perturb_norm_affines(sd, seed=7):
     for k, v in sd.items():
         if "layer_norm" in k and k.endswith(".weight"):
             v = v + 0.1 * torch.randn(v.shape, generator=g)
+        elif k.endswith("batch_norm.weight"):  # HuBERT conv_pos_batch_norm: exercise the running statistics too
+            v = v + 0.2 * torch.randn(v.shape, generator=g)
+        elif k.endswith("running_mean"):
+            v = v + 0.3 * torch.randn(v.shape, generator=g)
+        elif k.endswith("running_var"):
+            v = v * (0.5 + torch.rand(v.shape, generator=g))
         elif k.endswith("gru_rel_pos_const"):  # WavLM: ones at init
             v = v + 0.3 * torch.randn(v.shape, generator=g)
         elif k.endswith("rel_attn_embed.weight"):  # WavLM: make the position bias comparable to the scores
@@ -135,6 +141,9 @@ def gold_hubert(tmp):
     post-LN layers, NO LayerNorm in the feature projection; large = wav2vec2-large's graph."""
     gold_w2v2("hubert_base_1s", W2V2Config.hubert_base(), B=2, L=16000, tmp=tmp, store_weights=False)
     gold_w2v2("hubert_large_1s", W2V2Config.hubert_large(), B=1, L=16000, tmp=tmp, store_weights=False)
+    cfg = W2V2Config.hubert_base()
+    cfg.conv_pos_batch_norm = True
+    gold_w2v2("hubert_base_posbn_1s", cfg, B=2, L=16000, tmp=tmp, store_weights=False)
 
 
 def gold_wavlm(tmp):

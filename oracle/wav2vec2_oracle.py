@@ -57,6 +57,9 @@ class W2V2Config:
     # WavLM (HF modeling_wavlm.py, WavLMAttention): bucketed relative position bias, gated per query row
     num_buckets: int = 320
     max_bucket_distance: int = 800
+    # HuBERT variants with conv_pos_batch_norm (HF modeling_hubert.py, HubertPositionalConvEmbedding): BatchNorm1d before a
+    # plain positional conv instead of weight norm
+    conv_pos_batch_norm: bool = False
 
     @staticmethod
     def wavlm_base() -> "W2V2Config":
@@ -119,11 +122,13 @@ class W2V2Config:
                 type(cfg).__name__[:3], "wav2vec2"),
             num_buckets=int(getattr(cfg, "num_buckets", 320)),
             max_bucket_distance=int(getattr(cfg, "max_bucket_distance", 800)),
+            conv_pos_batch_norm=bool(getattr(cfg, "conv_pos_batch_norm", False)),
             conv_pos_kernel_size=int(getattr(cfg, "conv_pos_kernel_size", 19)),
         )
 
     def hf_kwargs(self) -> dict:
-        extra = {"feat_proj_layer_norm": self.feat_proj_layer_norm} if self.family == "hubert" else {}
+        extra = ({"feat_proj_layer_norm": self.feat_proj_layer_norm, "conv_pos_batch_norm": self.conv_pos_batch_norm}
+                 if self.family == "hubert" else {})
         if self.family == "data2vec":
             extra = {"conv_pos_kernel_size": self.conv_pos_kernel_size}
         if self.family == "wavlm":
@@ -279,9 +284,15 @@ def encoder(cfg: W2V2Config, sd, h, prefix="model.", taps: Optional[dict] = None
             pos = gelu(pos)
         pos = pos.transpose(1, 2)
     else:
-        w = pos_conv_weight(sd, prefix)
+        x = h.transpose(1, 2)
+        if cfg.conv_pos_batch_norm:  # eval-mode BatchNorm1d, then a plain conv
+            bn = e + "pos_conv_embed.batch_norm."
+            x = F.batch_norm(x, sd[bn + "running_mean"], sd[bn + "running_var"], sd[bn + "weight"], sd[bn + "bias"], False, 0.0, 1e-5)
+            w = sd[e + "pos_conv_embed.conv.weight"]
+        else:
+            w = pos_conv_weight(sd, prefix)
         kpos = cfg.num_conv_pos_embeddings
-        pos = F.conv1d(h.transpose(1, 2), w, sd[e + "pos_conv_embed.conv.bias"], padding=kpos // 2,
+        pos = F.conv1d(x, w, sd[e + "pos_conv_embed.conv.bias"], padding=kpos // 2,
                        groups=cfg.num_conv_pos_embedding_groups)
         if kpos % 2 == 0:
             pos = pos[:, :, :-1]  # HF:371-379 SamePad

@@ -19,6 +19,7 @@ class EncoderConfig(C.Structure):
         ("pos_conv_kernel", C.c_int), ("pos_conv_groups", C.c_int), ("layer_norm_eps", C.c_float),
         ("normalize_wav", C.c_int), ("output_norm", C.c_int), ("feat_proj_norm", C.c_int),
         ("pos_conv_layers", C.c_int), ("rel_pos_buckets", C.c_int), ("rel_pos_max_distance", C.c_int),
+        ("pos_conv_batch_norm", C.c_int),
     ]
 
 

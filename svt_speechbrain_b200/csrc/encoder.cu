@@ -239,6 +239,31 @@ int svt::encoder_finalize(svt_encoder* e) {
     }
     SVT_TRY(zero_vec(pool, D, 1.f, &e->ones));
     SVT_TRY(zero_vec(pool, D, 0.f, &e->zeros));
+  } else if (c.pos_conv_batch_norm) {
+    // HuBERT conv_pos_batch_norm: BatchNorm1d (running statistics) in front of a plain grouped conv
+    const int taps = c.pos_conv_kernel, Dg = D / c.pos_conv_groups;
+    const std::string bn = "encoder.pos_conv_embed.batch_norm.";
+    const RawTensor *w, *g, *b, *rm, *rv;
+    SVT_TRY(reg.require("encoder.pos_conv_embed.conv.weight", {D, Dg, taps}, &w));
+    SVT_TRY(reg.require(bn + "weight", {D}, &g));
+    SVT_TRY(reg.require(bn + "bias", {D}, &b));
+    SVT_TRY(reg.require(bn + "running_mean", {D}, &rm));
+    SVT_TRY(reg.require(bn + "running_var", {D}, &rv));
+    std::vector<float> hg(D), hb(D), hm(D), hv(D), sc(D), sh(D);
+    SVT_CUDA(cudaMemcpy(hg.data(), g->dev, sizeof(float) * D, cudaMemcpyDeviceToHost));
+    SVT_CUDA(cudaMemcpy(hb.data(), b->dev, sizeof(float) * D, cudaMemcpyDeviceToHost));
+    SVT_CUDA(cudaMemcpy(hm.data(), rm->dev, sizeof(float) * D, cudaMemcpyDeviceToHost));
+    SVT_CUDA(cudaMemcpy(hv.data(), rv->dev, sizeof(float) * D, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < D; ++i) {
+      sc[i] = hg[i] / std::sqrt(hv[i] + 1e-5f);  // nn.BatchNorm1d default eps
+      sh[i] = hb[i] - hm[i] * sc[i];
+    }
+    SVT_TRY(pool.alloc_t<float>(D, &e->pos_bn_scale));
+    SVT_TRY(pool.alloc_t<float>(D, &e->pos_bn_shift));
+    SVT_CUDA(cudaMemcpy(e->pos_bn_scale, sc.data(), sizeof(float) * D, cudaMemcpyHostToDevice));
+    SVT_CUDA(cudaMemcpy(e->pos_bn_shift, sh.data(), sizeof(float) * D, cudaMemcpyHostToDevice));
+    SVT_TRY(pack_pos(w, nullptr, &e->pos_w));
+    SVT_TRY(pack_vec(pool, reg, "encoder.pos_conv_embed.conv.bias", D, 1.f, &e->pos_b));
   } else {
     // weight-norm recomposition folded here (HF:343-355)
     const int taps = c.pos_conv_kernel, Dg = D / c.pos_conv_groups;
@@ -432,7 +457,8 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
     return g;
   };
   if (c.pos_conv_layers == 0) {
-    // ---- positional conv embedding + residual: h += GELU(conv(h) + b)
+    // ---- positional conv embedding + residual: h += GELU(conv(h) + b)   (HuBERT conv_pos_batch_norm: conv(BN(h)))
+    if (c.pos_conv_batch_norm) SVT_TRY(channel_affine_bf16(h, e->pos_bn_scale, e->pos_bn_shift, hb, M, D, s));
     GemmArgs g = pos_conv(hb, e->pos_w, e->pos_b);
     g.resid = h; g.out_f32 = h; g.act = kActGelu;
     SVT_TRY(gemm_bf16_tc(g, s));

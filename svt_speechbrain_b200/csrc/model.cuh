@@ -106,6 +106,8 @@ struct svt_encoder {
   float* pos_b = nullptr;
   struct PosLayer { __nv_bfloat16* w = nullptr; float* b = nullptr; };
   std::vector<PosLayer> pos_stack;  // data2vec-audio: cfg.pos_conv_layers x (conv weights as pos_w, bias)
+  float* pos_bn_scale = nullptr;    // HuBERT conv_pos_batch_norm: gamma / sqrt(running_var + eps), beta - mean * that
+  float* pos_bn_shift = nullptr;
   float* ones = nullptr;            // [D] affine of the stack's parameter-free LayerNorms
   float* zeros = nullptr;
   svt::NormW enc_norm;

@@ -128,5 +128,8 @@ int add_positional_encoding(const float* x, int clips, int T_src, int T, int D, 
 // out = a + b (fp32, n elements)
 int add_f32(const float* a, const float* b, float* out, size_t n, cudaStream_t stream);
 int cast_f32_to_bf16(const float* x, __nv_bfloat16* y, size_t n, cudaStream_t stream);
+// y[row][c] = bf16(x[row][c] * scale[c] + shift[c]): eval-mode BatchNorm1d over channel-last rows
+int channel_affine_bf16(const float* x, const float* scale, const float* shift, __nv_bfloat16* y, size_t rows, int D,
+                        cudaStream_t stream);
 
 }  // namespace svt

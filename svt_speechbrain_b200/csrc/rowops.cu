@@ -358,6 +358,19 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
     y[i] = __float2bfloat16(x[i]);
 }
 
+// y[row][c] = bf16(x[row][c] * scale[c] + shift[c])  (eval-mode BatchNorm1d over channel-last rows)
+__global__ void channel_affine_bf16_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                           const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, size_t n4, int D4) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int c = static_cast<int>(i % D4) * 4;
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+    st_bf16x4(y + i * 4, fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+  }
+}
+
 template <typename OutT>
 __global__ void pack_kernel(const float* __restrict__ src, int d0, int d1, int d2, int d3, long long s0, long long s1,
                             long long s2, long long s3, float scale, const float* __restrict__ vec, int vec_dim,
@@ -646,6 +659,13 @@ int add_positional_encoding(const float* x, int clips, int T_src, int T, int D, 
 
 int add_f32(const float* a, const float* b, float* out, size_t n, cudaStream_t stream) {
   add_f32_kernel<<<num_sms() * 4, 256, 0, stream>>>(a, b, out, n);
+  SVT_POST_LAUNCH();
+  return kOk;
+}
+int channel_affine_bf16(const float* x, const float* scale, const float* shift, __nv_bfloat16* y, size_t rows, int D,
+                        cudaStream_t stream) {
+  if (D % 4 != 0) return fail(kInvalidArgument, "channel_affine: D % 4 != 0");
+  channel_affine_bf16_kernel<<<num_sms() * 4, 256, 0, stream>>>(x, scale, shift, y, rows * (D / 4), D / 4);
   SVT_POST_LAUNCH();
   return kOk;
 }

@@ -44,6 +44,7 @@ def encoder_config_from_hf(cfg, normalize_wav: bool, output_norm: bool) -> Encod
         raise NotImplementedError("only the exact-erf GELU activation of wav2vec2/HuBERT is built")
     c.normalize_wav = int(bool(normalize_wav))
     c.output_norm = int(bool(output_norm))
+    c.pos_conv_batch_norm = int(bool(getattr(cfg, "conv_pos_batch_norm", False)))  # HubertConfig only
     if type(cfg).__name__.startswith("WavLM"):
         c.rel_pos_buckets = cfg.num_buckets
         c.rel_pos_max_distance = cfg.max_bucket_distance

@@ -50,11 +50,9 @@ class HuggingFaceWav2Vec2(nn.Module):
             # the reference falls through to an UnboundLocalError here; keep "unknown source" loud but clearer
             raise UnboundLocalError(f"cannot pick a model family from source={source!r} (expected 'wav2vec2' or 'hubert')")
         if family not in _FAMILIES:
-            raise NotImplementedError(f"{family}: not built yet in svt_speechbrain_b200 (wav2vec2, HuBERT and data2vec-audio are)")
+            raise NotImplementedError(f"{family}: not a family of the reference lobe (wav2vec2, hubert, data2vec, wavlm)")
         config_cls, model_cls = _FAMILIES[family]
         config = config_cls.from_pretrained(source, cache_dir=save_path)
-        if family == "hubert" and getattr(config, "conv_pos_batch_norm", False):
-            raise NotImplementedError("HuBERT conv_pos_batch_norm variants are not built")
         config.apply_spec_augment = apply_spec_augment  # inert at eval (HF:1292)
         if pretrain:
             self._check_model_source(source)

@@ -27,8 +27,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_config_struct_layout_matches_header():
-    # 6 ints + 2 * 8 ints + 5 ints + float + 6 ints
-    assert C.sizeof(_lib.EncoderConfig) == 4 * (6 + 16 + 5 + 1 + 6)
+    # 6 ints + 2 * 8 ints + 5 ints + float + 7 ints
+    assert C.sizeof(_lib.EncoderConfig) == 4 * (6 + 16 + 5 + 1 + 7)
     assert C.sizeof(_lib.FusionConfig) == 16
 
 

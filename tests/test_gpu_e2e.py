@@ -52,7 +52,8 @@ def _check_logits(got, ref, tag):
 
 
 @pytest.mark.parametrize("name", ["w2v2_large_1s", "w2v2_base_1s", "w2v2_large_5s", "hubert_base_1s", "hubert_large_1s",
-                                  "data2vec_base_1s", "wavlm_base_1s", "wavlm_large_1s", "wavlm_base_5s"])
+                                  "data2vec_base_1s", "wavlm_base_1s", "wavlm_large_1s", "wavlm_base_5s",
+                                  "hubert_base_posbn_1s"])
 def test_encoder_vs_reference_golden(name):
     from oracle import make_golden as mg
     from oracle import wav2vec2_oracle as wo
@@ -61,7 +62,9 @@ def test_encoder_vs_reference_golden(name):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     cfg = {"w2v2_base": wo.W2V2Config.base, "w2v2_large": wo.W2V2Config.large, "hubert_base": wo.W2V2Config.hubert_base,
            "hubert_large": wo.W2V2Config.hubert_large, "data2vec_base": wo.W2V2Config.data2vec_base,
-           "wavlm_base": wo.W2V2Config.wavlm_base, "wavlm_large": wo.W2V2Config.wavlm_large}[name.rsplit("_", 1)[0]]()
+           "wavlm_base": wo.W2V2Config.wavlm_base, "wavlm_large": wo.W2V2Config.wavlm_large,
+           "hubert_base_posbn": lambda: wo.W2V2Config(family="hubert", feat_proj_layer_norm=False, conv_pos_batch_norm=True),
+           }[name.rsplit("_", 1)[0]]()
     lobe, lin, sd, head = _build(cfg)
     wav = mg.synth_wav(int(g["B"]), int(g["L"]), seed=int(g["wav_seed"])).cuda()
     # (1) module-by-module, exactly like AMT.compute_forward: feats = lobe(wav); logits = head(feats)

@@ -34,6 +34,8 @@ def test_tiny_stored_weights(name, cfg):
                                       ("hubert_base_1s", wo.W2V2Config.hubert_base()),
                                       ("hubert_large_1s", wo.W2V2Config.hubert_large()),
                                       ("data2vec_base_1s", wo.W2V2Config.data2vec_base()),
+                                      ("hubert_base_posbn_1s", wo.W2V2Config(family="hubert", feat_proj_layer_norm=False,
+                                                                             conv_pos_batch_norm=True)),
                                       ("wavlm_base_1s", wo.W2V2Config.wavlm_base()),
                                       ("wavlm_large_1s", wo.W2V2Config.wavlm_large()),
                                       ("wavlm_base_5s", wo.W2V2Config.wavlm_base())])

@@ -120,6 +120,19 @@ int svt_encoder_forward_host(svt_encoder* enc, const float* wav_host, int batch,
                              size_t workspace_bytes, float* wav_stage_dev, float* logits_stage_dev,
                              float* logits_host, void* stream);
 
+/* ------------------------------------------------------------------ host-buffer serving pipeline
+ * The reference's evaluation loop hands one HOST batch at a time to the model (speechbrain/core.py:1221-1226).  A
+ * pipeline keeps `depth` batches in flight: the H2D copy of batch k + 1 runs on a copy stream under the forward of
+ * batch k, the D2H of its logits follows on the compute stream.  Memory is the caller's: workspace as for
+ * svt_encoder_forward, wav_stage_dev depth x (batch x n_samples) floats, logits_stage_dev depth x (batch x T x n_out)
+ * floats; host buffers must be pinned and stay valid until svt_pipeline_wait(ticket) returns.  Needs a head. */
+typedef struct svt_pipeline svt_pipeline;
+int svt_pipeline_create(svt_encoder* enc, int batch, int n_samples, int depth, void* workspace_dev, size_t workspace_bytes,
+                        float* wav_stage_dev, float* logits_stage_dev, svt_pipeline** out);
+void svt_pipeline_destroy(svt_pipeline* p);
+int svt_pipeline_submit(svt_pipeline* p, const float* wav_host_pinned, float* logits_host_pinned, long long* ticket);
+int svt_pipeline_wait(svt_pipeline* p, long long ticket);
+
 /* ------------------------------------------------------------------ residual cross-attention fusion */
 typedef struct svt_fusion svt_fusion;
 typedef struct svt_fusion_config {

@@ -59,6 +59,10 @@ _SIGS = {
     "svt_encoder_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
     "svt_encoder_forward": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P, _P, _P]),
     "svt_encoder_forward_host": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P, _P, _P, _P]),
+    "svt_pipeline_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P, _P, C.POINTER(_P)]),
+    "svt_pipeline_destroy": (None, [_P]),
+    "svt_pipeline_submit": (C.c_int, [_P, _P, _P, C.POINTER(C.c_longlong)]),
+    "svt_pipeline_wait": (C.c_int, [_P, C.c_longlong]),
     "svt_fusion_create": (C.c_int, [C.POINTER(FusionConfig), C.POINTER(_P)]),
     "svt_fusion_destroy": (None, [_P]),
     "svt_fusion_set_tensor": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, C.c_int]),

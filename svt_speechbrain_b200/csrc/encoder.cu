@@ -781,4 +781,92 @@ int svt_encoder_forward_host(svt_encoder* enc, const float* wav_host, int batch,
   return kOk;
 }
 
+// ------------------------------------------------------------------------------------ host-buffer pipeline
+// Serving loop for HOST batches: the H2D copy of batch k + 1 runs on its own stream under the forward of batch k, the
+// D2H of the logits follows the forward on the compute stream.  Caller-owned memory, library-owned streams / events.
+struct svt_pipeline {
+  svt_encoder* enc = nullptr;
+  int B = 0, L = 0, T = 0, depth = 0;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  float* wav_stage = nullptr;
+  float* logits_stage = nullptr;
+  cudaStream_t copy = nullptr, compute = nullptr;
+  std::vector<cudaEvent_t> h2d, free_, done;
+  long long submitted = 0;
+};
+
+int svt_pipeline_create(svt_encoder* enc, int batch, int n_samples, int depth, void* workspace_dev, size_t workspace_bytes,
+                        float* wav_stage_dev, float* logits_stage_dev, svt_pipeline** out) {
+  if (enc == nullptr || out == nullptr || workspace_dev == nullptr || wav_stage_dev == nullptr || logits_stage_dev == nullptr)
+    return fail(kInvalidArgument, "null argument");
+  if (!enc->finalized || enc->head_w == nullptr) return fail(kNotFinalized, "pipeline: encoder must be finalized and have a head");
+  if (batch <= 0 || n_samples <= 0 || depth < 1 || depth > 8) return fail(kInvalidArgument, "pipeline: bad batch / samples / depth");
+  const EncPlan p = make_plan(enc, batch, n_samples);
+  if (p.Tn <= 0) return fail(kInvalidArgument, "input too short for the conv stack");
+  if (workspace_bytes < p.total) return fail(kWorkspaceTooSmall, "workspace too small: need " + std::to_string(p.total));
+  svt_pipeline* pl = new svt_pipeline();
+  pl->enc = enc; pl->B = batch; pl->L = n_samples; pl->T = p.Tn; pl->depth = depth;
+  pl->ws = workspace_dev; pl->ws_bytes = workspace_bytes; pl->wav_stage = wav_stage_dev; pl->logits_stage = logits_stage_dev;
+  if (cudaStreamCreateWithFlags(&pl->copy, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&pl->compute, cudaStreamNonBlocking) != cudaSuccess) {
+    delete pl;
+    return fail(kCudaError, "pipeline: cannot create streams");
+  }
+  pl->h2d.resize(depth); pl->free_.resize(depth); pl->done.resize(depth);
+  for (int i = 0; i < depth; ++i) {
+    cudaEventCreateWithFlags(&pl->h2d[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&pl->free_[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&pl->done[i], cudaEventDisableTiming);
+  }
+  *out = pl;
+  return kOk;
+}
+
+void svt_pipeline_destroy(svt_pipeline* pl) {
+  if (pl == nullptr) return;
+  if (pl->compute != nullptr) cudaStreamSynchronize(pl->compute);
+  if (pl->copy != nullptr) cudaStreamSynchronize(pl->copy);
+  for (auto e : pl->h2d) cudaEventDestroy(e);
+  for (auto e : pl->free_) cudaEventDestroy(e);
+  for (auto e : pl->done) cudaEventDestroy(e);
+  if (pl->copy != nullptr) cudaStreamDestroy(pl->copy);
+  if (pl->compute != nullptr) cudaStreamDestroy(pl->compute);
+  delete pl;
+}
+
+int svt_pipeline_submit(svt_pipeline* pl, const float* wav_host_pinned, float* logits_host_pinned, long long* ticket) {
+  if (pl == nullptr || wav_host_pinned == nullptr || logits_host_pinned == nullptr || ticket == nullptr)
+    return fail(kInvalidArgument, "null argument");
+  const long long k = pl->submitted;
+  const int slot = static_cast<int>(k % pl->depth);
+  const size_t in_elems = static_cast<size_t>(pl->B) * pl->L;
+  const size_t out_elems = static_cast<size_t>(pl->B) * pl->T * pl->enc->head_n;
+  float* wav_dev = pl->wav_stage + static_cast<size_t>(slot) * in_elems;
+  float* lg_dev = pl->logits_stage + static_cast<size_t>(slot) * out_elems;
+  if (k >= pl->depth) {
+    // the slot's previous occupant must have left the device: its forward no longer reads wav_dev, its D2H is complete
+    SVT_CUDA(cudaStreamWaitEvent(pl->copy, pl->free_[slot], 0));
+    SVT_CUDA(cudaEventSynchronize(pl->done[slot]));
+  }
+  SVT_CUDA(cudaMemcpyAsync(wav_dev, wav_host_pinned, sizeof(float) * in_elems, cudaMemcpyHostToDevice, pl->copy));
+  SVT_CUDA(cudaEventRecord(pl->h2d[slot], pl->copy));
+  SVT_CUDA(cudaStreamWaitEvent(pl->compute, pl->h2d[slot], 0));
+  SVT_TRY(forward_impl(pl->enc, wav_dev, pl->B, pl->L, pl->ws, pl->ws_bytes, nullptr, lg_dev, pl->compute));
+  SVT_CUDA(cudaEventRecord(pl->free_[slot], pl->compute));
+  SVT_CUDA(cudaMemcpyAsync(logits_host_pinned, lg_dev, sizeof(float) * out_elems, cudaMemcpyDeviceToHost, pl->compute));
+  SVT_CUDA(cudaEventRecord(pl->done[slot], pl->compute));
+  *ticket = k;
+  pl->submitted = k + 1;
+  return kOk;
+}
+
+int svt_pipeline_wait(svt_pipeline* pl, long long ticket) {
+  if (pl == nullptr) return fail(kInvalidArgument, "null argument");
+  if (ticket < 0 || ticket >= pl->submitted) return fail(kInvalidArgument, "pipeline: unknown ticket");
+  if (ticket + pl->depth < pl->submitted) return kOk;  // its slot has been reused: that only happens after completion
+  SVT_CUDA(cudaEventSynchronize(pl->done[static_cast<int>(ticket % pl->depth)]));
+  return kOk;
+}
+
 }  // extern "C"

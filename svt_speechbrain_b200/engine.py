@@ -134,11 +134,69 @@ class EncoderEngine:
             check(lib().svt_encoder_forward_host(self._h, ptr(wav_host), B, L, ptr(ws), ws.numel(), ptr(wav_stage),
                                                  ptr(logits_stage), ptr(logits_host), current_stream_ptr()))
 
+    def pipeline(self, batch: int, n_samples: int, depth: int = 2) -> "EncoderPipeline":
+        """Serving loop for pinned HOST batches of one shape (svt_pipeline_*): copies overlap the previous batch's forward."""
+        return EncoderPipeline(self, batch, n_samples, depth)
+
     def __del__(self):
         try:
             if self._h:
                 lib().svt_encoder_destroy(self._h)
                 self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
+class EncoderPipeline:
+    """`depth` host batches in flight through svt_pipeline_submit / svt_pipeline_wait.
+
+        pipe = engine.pipeline(B, L)
+        t = pipe.submit(wav_pinned, logits_pinned)     # returns at once; (B, L) fp32 pinned -> (B, T, n_out) fp32 pinned
+        ...                                            # submit the next batch before waiting: that is the overlap
+        pipe.wait(t)                                   # logits_pinned is complete
+    """
+
+    def __init__(self, engine: EncoderEngine, batch: int, n_samples: int, depth: int = 2):
+        self.engine, self.B, self.L, self.depth = engine, batch, n_samples, depth
+        self.T = engine.num_frames(n_samples)
+        if self.T <= 0:
+            raise ValueError("input too short for the conv feature extractor")
+        if engine.n_out <= 0:
+            raise RuntimeError("no head set")
+        dev = engine.device
+        need = lib().svt_encoder_workspace_bytes(engine._h, batch, n_samples)
+        self._ws = torch.empty(need, dtype=torch.uint8, device=dev)  # private: engine.forward may run concurrently
+        self._wav = torch.empty(depth, batch, n_samples, dtype=torch.float32, device=dev)
+        self._lg = torch.empty(depth, batch, self.T, engine.n_out, dtype=torch.float32, device=dev)
+        self._h = C.c_void_p()
+        with torch.cuda.device(dev):
+            torch.cuda.synchronize(dev)  # the pipeline's own streams do not order against torch's allocator streams
+            check(lib().svt_pipeline_create(engine._h, batch, n_samples, depth, ptr(self._ws), self._ws.numel(), ptr(self._wav),
+                                            ptr(self._lg), C.byref(self._h)))
+
+    def _check_host(self, t: torch.Tensor, shape, what: str):
+        if t.is_cuda or not t.is_pinned() or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{what}: expected a pinned contiguous fp32 host tensor of shape {tuple(shape)}")
+
+    def submit(self, wav_host: torch.Tensor, logits_host: torch.Tensor) -> int:
+        self._check_host(wav_host, (self.B, self.L), "wav_host")
+        self._check_host(logits_host, (self.B, self.T, self.engine.n_out), "logits_host")
+        ticket = C.c_longlong(-1)
+        with torch.cuda.device(self.engine.device):
+            check(lib().svt_pipeline_submit(self._h, ptr(wav_host), ptr(logits_host), C.byref(ticket)))
+        return ticket.value
+
+    def wait(self, ticket: int):
+        check(lib().svt_pipeline_wait(self._h, ticket))
+
+    def close(self):
+        if self._h:
+            lib().svt_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass
 

@@ -281,3 +281,33 @@ def test_feature_cache_stage_a_equals_batch_size_one_extraction(tmp_path):
     assert rel < 2e-2
     p = fc.save_song_features(feats, fc.audio_feats_path(str(tmp_path / "song")))
     assert torch.equal(torch.load(p), feats)
+
+
+def test_host_pipeline_overlapped_batches_equal_plain_forward():
+    """svt_pipeline_*: five different pinned host batches through a depth-2 pipeline (staging slots reused twice) give
+    exactly the logits of the plain device-resident forward of the same batches."""
+    from oracle import wav2vec2_oracle as wo
+    import svt_speechbrain_b200 as svt
+
+    cfg = wo.W2V2Config.large()
+    lobe, lin, sd, head = _build(cfg)
+    tr = svt.AMTTranscriber(lobe, lin)
+    eng = tr._engine()
+    B, L = 3, 16000
+    g = torch.Generator().manual_seed(21)
+    wavs = [(torch.randn(B, L, generator=g) * (0.5 + i)).pin_memory() for i in range(5)]
+    T = eng.num_frames(L)
+    outs = [torch.empty(B, T, 20).pin_memory() for _ in range(5)]
+    pipe = eng.pipeline(B, L, depth=2)
+    tickets = [pipe.submit(w, o) for w, o in zip(wavs, outs)]
+    assert tickets == [0, 1, 2, 3, 4]
+    for t in reversed(tickets):  # any order; old tickets whose slot was reused are already complete
+        pipe.wait(t)
+    for w, o in zip(wavs, outs):
+        ref = tr.logits(w.cuda()).cpu()
+        assert torch.equal(o, ref)
+    with pytest.raises(ValueError):
+        pipe.submit(torch.randn(B, L), outs[0])  # not pinned
+    with pytest.raises(svt.SvtError):
+        pipe.wait(99)
+    pipe.close()

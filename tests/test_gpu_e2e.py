@@ -311,3 +311,53 @@ def test_host_pipeline_overlapped_batches_equal_plain_forward():
     with pytest.raises(svt.SvtError):
         pipe.wait(99)
     pipe.close()
+
+
+@pytest.mark.parametrize("family", ["large", "base"])
+def test_edge_lengths_vs_oracle(family):
+    """Shortest clips the conv stack accepts (1, 2, 3 output frames), a ragged odd length, and a 20-s clip (999 frames:
+    eight key blocks in the attention kernel, eight 125-frame tiles in the positional conv), against the oracle."""
+    from oracle import wav2vec2_oracle as wo
+
+    cfg = wo.W2V2Config.large() if family == "large" else wo.W2V2Config.base()
+    lobe, lin, sd, head = _build(cfg)
+    cases = [(2, 400), (1, 720), (3, 1040), (2, 7777), (1, 320000)]
+    for B, L in cases:
+        wav = torch.randn(B, L, generator=torch.Generator().manual_seed(L))
+        T = cfg.num_frames(L)
+        with torch.no_grad():
+            ref = wo.amt_logits(cfg, sd, head, wav).numpy()
+        got = lin(lobe(wav.cuda()))
+        assert got.shape == (B, T, 20)
+        _check_logits(got, ref, f"{family} B={B} L={L} (T={T})")
+    with pytest.raises(Exception):
+        lobe(torch.randn(1, 399).cuda())  # shorter than the receptive field: no output frame
+
+
+def test_c_abi_error_paths_on_device():
+    """Workspace too small, logits without a head, not-finalized handle: error codes + messages, no device traps."""
+    import ctypes as C
+    from oracle import wav2vec2_oracle as wo
+    from svt_speechbrain_b200._lib import lib, ptr, current_stream_ptr
+    from svt_speechbrain_b200.engine import EncoderEngine, encoder_config_from_hf
+    from transformers import Wav2Vec2Config
+
+    cfg = wo.W2V2Config.base()
+    eng = EncoderEngine(encoder_config_from_hf(Wav2Vec2Config(**cfg.hf_kwargs()), True, True), torch.device("cuda"))
+    wav = torch.randn(1, 16000, device="cuda")
+    feats = torch.empty(1, 49, 768, device="cuda")
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    L = lib()
+    rc = L.svt_encoder_forward(eng._h, ptr(wav), 1, 16000, ptr(ws), ws.numel(), ptr(feats), None, current_stream_ptr())
+    assert rc != 0 and b"finalize" in L.svt_last_error()
+    eng.load(wo.random_weights(cfg, seed=0))
+    rc = L.svt_encoder_forward(eng._h, ptr(wav), 1, 16000, ptr(ws), ws.numel(), ptr(feats), None, current_stream_ptr())
+    assert rc != 0 and b"workspace too small" in L.svt_last_error()
+    big = eng.workspace(1, 16000)
+    lg = torch.empty(1, 49, 20, device="cuda")
+    rc = L.svt_encoder_forward(eng._h, ptr(wav), 1, 16000, ptr(big), big.numel(), None, ptr(lg), current_stream_ptr())
+    assert rc != 0 and b"no head" in L.svt_last_error()
+    rc = L.svt_encoder_forward(eng._h, ptr(wav), 1, 16000, ptr(big), big.numel(), ptr(feats), None, current_stream_ptr())
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.isfinite(feats).all()

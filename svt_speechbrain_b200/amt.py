@@ -47,6 +47,43 @@ def split_song(n_samples: int, hp: AMTHparams, dur: Optional[float] = None) -> L
     return out
 
 
+FRAME_HOP = 320      # samples between output frames of the conv stack (product of the strides 5 * 2^6)
+FRAME_FIELD = 400    # receptive field of one output frame
+
+
+def split_song_overlapped(n_samples: int, sample_rate: int, dur: float, overlap: float) -> List[Tuple[int, int]]:
+    """Sliding windows of `dur` seconds every `dur - overlap` seconds (BASELINE config 5: long-form songs cut into
+    overlapping windows).  Window starts are multiples of the frame hop so the windows' frames sit on one global frame
+    grid; the last window ends at the end of the song."""
+    if not 0 <= overlap < dur:
+        raise ValueError("need 0 <= overlap < dur")
+    win = int(round(dur * sample_rate))
+    hop = max(FRAME_HOP, int(round((dur - overlap) * sample_rate)) // FRAME_HOP * FRAME_HOP)
+    out, a = [], 0
+    while True:
+        b = min(a + win, n_samples)
+        out.append((a, b))
+        if b >= n_samples:
+            return out
+        a += hop
+
+
+def stitch_plan(windows: Sequence[Tuple[int, int]]) -> List[Tuple[int, int]]:
+    """Per window, the [lo, hi) range of its LOCAL frames kept in the stitched song: consecutive windows meet in the
+    middle of their overlap (first / last window keep their outer ends), so every global frame comes from the window in
+    which it is furthest from an edge.  Frame f of a window starting at sample a is global frame a / hop + f."""
+    n = [max((b - a - FRAME_FIELD) // FRAME_HOP + 1, 0) for a, b in windows]
+    g0 = [a // FRAME_HOP for a, _ in windows]
+    plan = []
+    for i in range(len(windows)):
+        lo_g = g0[i] if i == 0 else (g0[i] + g0[i - 1] + n[i - 1] + 1) // 2
+        hi_g = g0[i] + n[i] if i == len(windows) - 1 else (g0[i + 1] + g0[i] + n[i] + 1) // 2
+        lo_g = max(lo_g, g0[i])
+        hi_g = min(max(hi_g, lo_g), g0[i] + n[i])
+        plan.append((lo_g - g0[i], hi_g - g0[i]))
+    return plan
+
+
 class AMTTranscriber:
     """lobe: svt_speechbrain_b200.HuggingFaceWav2Vec2; head: svt_speechbrain_b200.Linear (n_neurons = 20)."""
 
@@ -127,6 +164,46 @@ class AMTTranscriber:
             pieces.extend(lg[k] for k in range(lg.shape[0]))
             i = j
         return self.decode(torch.cat(pieces, dim=0))
+
+    @torch.no_grad()
+    def transcribe_long(self, wav: torch.Tensor, dur: float = 10.0, overlap: float = 1.0, batch_clips: int = 64,
+                        per_clip_norm: bool = True, group=None) -> np.ndarray:
+        """Long-form song (BASELINE config 5): overlapping `dur`-second windows, sharded over the ranks of `group` when
+        torch.distributed is initialised (contiguous blocks of windows per rank, no collective inside the forward), frame
+        logits gathered in window order, overlaps resolved by `stitch_plan`, one decode of the stitched frames (identical
+        on every rank).  overlap = 0 on a song whose length is a multiple of `dur` is `transcribe_song`."""
+        return self.decode(self.long_form_logits(wav, dur, overlap, batch_clips, per_clip_norm, group))
+
+    @torch.no_grad()
+    def long_form_logits(self, wav: torch.Tensor, dur: float = 10.0, overlap: float = 1.0, batch_clips: int = 64,
+                         per_clip_norm: bool = True, group=None) -> torch.Tensor:
+        """The stitched (n_frames, 20) frame logits behind `transcribe_long` (same on every rank)."""
+        import torch.distributed as dist
+        from .parallel import gather_ragged, shard_range
+
+        wav = wav.to(self.device, torch.float32).reshape(-1)
+        windows = split_song_overlapped(wav.numel(), self.hp.sample_rate, dur, overlap)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        lo, hi = shard_range(len(windows), rank, world)
+        mine = windows[lo:hi]
+        local: List[torch.Tensor] = []
+        i = 0
+        while i < len(mine):
+            j = i
+            L = mine[i][1] - mine[i][0]
+            while j < len(mine) and j - i < batch_clips and mine[j][1] - mine[j][0] == L:
+                j += 1
+            clips = torch.stack([wav[a:b] for a, b in mine[i:j]])
+            if per_clip_norm and j - i > 1 and L % 4 != 0:
+                lg = torch.cat([self.logits(c.unsqueeze(0)) for c in clips], dim=0)
+            else:
+                lg = self.logits(clips, per_clip_norm=per_clip_norm and j - i > 1)
+            local.extend(lg[k] for k in range(lg.shape[0]))
+            i = j
+        pieces = gather_ragged(local, len(windows), group) if world > 1 else local
+        plan = stitch_plan(windows)
+        return torch.cat([p[a:b] for p, (a, b) in zip(pieces, plan)], dim=0)
 
     @torch.no_grad()
     def transcribe_songs(self, wavs: Sequence[torch.Tensor], dur: Optional[float] = None, batch_clips: int = 64,

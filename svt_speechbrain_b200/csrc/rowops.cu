@@ -558,7 +558,9 @@ int tensor_stats_per_clip(const float* x, int clips, size_t n_per_clip, double* 
   SVT_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(double) * clips, stream));
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || n_per_clip % 4 != 0)
     return fail(kInvalidArgument, "per-clip statistics need 16-byte aligned clips (n_samples % 4 == 0)");
-  int gx = (num_sms() * 4 + clips - 1) / clips;
+  // CTAs per clip depend on the clip length only, never on the batch: a clip's partial sums (and so its statistics and
+  // everything downstream) are the same whichever batch or rank it is processed in
+  int gx = static_cast<int>(std::min<size_t>((n_per_clip / 4 + 4095) / 4096, 1024));
   if (gx < 1) gx = 1;
   tensor_stats_kernel<<<dim3(gx, clips), 256, 0, stream>>>(x, n_per_clip, stats, n_per_clip, 2);
   SVT_POST_LAUNCH();

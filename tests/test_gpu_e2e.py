@@ -361,3 +361,27 @@ def test_c_abi_error_paths_on_device():
     assert rc == 0
     torch.cuda.synchronize()
     assert torch.isfinite(feats).all()
+
+
+def test_long_form_windows_stitched_vs_oracle():
+    """transcribe_long / long_form_logits (BASELINE config 5 on one GPU): without overlap on a whole number of windows it is
+    transcribe_song; with overlap the stitched frames match the oracle run window by window and stitched by the same plan."""
+    import svt_speechbrain_b200 as svt
+    from oracle import wav2vec2_oracle as wo
+    from svt_speechbrain_b200.amt import AMTHparams, split_song_overlapped, stitch_plan
+
+    cfg = wo.W2V2Config.base()
+    lobe, lin, sd, head = _build(cfg)
+    tr = svt.AMTTranscriber(lobe, lin, AMTHparams(dur_threshold=2.0))
+    wav = torch.randn(16000 * 6, generator=torch.Generator().manual_seed(9))
+    a = tr.transcribe_long(wav, dur=2.0, overlap=0.0)
+    b = tr.transcribe_song(wav, dur=2.0)
+    assert np.array_equal(a, b)
+    wav = torch.randn(16000 * 7 + 913, generator=torch.Generator().manual_seed(10))
+    got = tr.long_form_logits(wav, dur=2.0, overlap=0.5).cpu()
+    windows = split_song_overlapped(wav.numel(), 16000, 2.0, 0.5)
+    with torch.no_grad():
+        ref = torch.cat([wo.amt_logits(cfg, sd, head, wav[s:e].unsqueeze(0))[0][lo:hi]
+                         for (s, e), (lo, hi) in zip(windows, stitch_plan(windows))])
+    assert got.shape == ref.shape == ((wav.numel() - 400) // 320 + 1, 20)
+    _check_logits(got, ref.numpy(), "long-form stitched logits")

@@ -1,0 +1,71 @@
+"""Long-form windowing / stitching arithmetic (BASELINE config 5) and the ragged multi-rank gather, CPU only."""
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from svt_speechbrain_b200.amt import FRAME_FIELD, FRAME_HOP, split_song_overlapped, stitch_plan
+
+
+@pytest.mark.parametrize("n,dur,overlap", [(16000 * 300 + 1234, 10.0, 1.0), (16000 * 30, 10.0, 0.0), (16000 * 47 + 7, 5.0, 2.5),
+                                           (16000 * 3, 10.0, 1.0), (16000 * 20 + 399, 10.0, 0.5)])
+def test_windows_tile_the_frame_grid(n, dur, overlap):
+    w = split_song_overlapped(n, 16000, dur, overlap)
+    assert w[0][0] == 0 and w[-1][1] == n and all(a % FRAME_HOP == 0 for a, _ in w)
+    assert all(b - a == int(dur * 16000) for a, b in w[:-1])
+    plan = stitch_plan(w)
+    if overlap == 0.0:
+        # the reference's evaluation rule: every window keeps all of its frames (one frame per boundary is never computed)
+        assert plan == [(0, (b - a - FRAME_FIELD) // FRAME_HOP + 1) for a, b in w]
+        return
+    g = 0
+    for (a, b), (lo, hi) in zip(w, plan):
+        nf = max((b - a - FRAME_FIELD) // FRAME_HOP + 1, 0)
+        assert 0 <= lo <= hi <= nf
+        if hi > lo:
+            assert a // FRAME_HOP + lo == g      # every global frame exactly once, in order
+            g = a // FRAME_HOP + hi
+    assert g == (n - FRAME_FIELD) // FRAME_HOP + 1  # as many frames as one pass over the whole song would give
+
+
+def test_kept_frames_stay_away_from_window_edges():
+    w = split_song_overlapped(16000 * 100, 16000, 10.0, 2.0)
+    plan = stitch_plan(w)
+    for i, ((a, b), (lo, hi)) in enumerate(zip(w, plan)):
+        nf = (b - a - FRAME_FIELD) // FRAME_HOP + 1
+        if 0 < i < len(w) - 1:
+            assert lo >= 45 and nf - hi >= 45     # ~1 s = half the overlap dropped on both sides
+
+
+def _worker(rank, world, port, n_total, q):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from svt_speechbrain_b200.parallel import gather_ragged, shard_range
+    lens = [5 + (3 * i) % 4 for i in range(n_total)]
+    items = [torch.full((lens[i], 20), float(i)) + torch.arange(lens[i])[:, None] / 100 for i in range(n_total)]
+    a, b = shard_range(n_total, rank, world)
+    got = gather_ragged([t.clone() for t in items[a:b]], n_total)
+    ok = len(got) == n_total and all(torch.equal(x, y) for x, y in zip(got, items))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [7, 1])
+def test_gather_ragged_two_ranks(n_total):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)

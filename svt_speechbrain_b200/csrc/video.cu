@@ -28,7 +28,8 @@ namespace {
 
 constexpr int kImg = 88;       // lip ROI (reference crops to 88 x 88, video_only/train_video_ssl.py:445-457)
 constexpr int kF0 = 44;        // after the stride-2 Conv3d
-constexpr int kFrontK = 256;   // 5 * 7 * 7 = 245 taps padded to a multiple of 64
+constexpr int kFrontK = 64;    // 7 * 7 = 49 spatial taps of one frame padded to 64; the 5 temporal taps are row shifts
+constexpr int kFrontT = 5;     // temporal taps of the Conv3d
 constexpr int kRes[4] = {22, 11, 6, 3};
 constexpr int kPlanes[4] = {64, 128, 256, 512};
 constexpr float kBnEps = 1e-5f;
@@ -46,19 +47,19 @@ struct ConvW {
 };
 
 // ------------------------------------------------------------------------------------------ kernels
-// Patch matrix of the Conv3d front end: row (n, y, x) = frame slot n = b * Ta + t, output pixel (y, x) of 44 x 44;
-// column k = (dt * 7 + dy) * 7 + dx < 245 holds video[b, t + dt - 2, 2y + dy - 3, 2x + dx - 3] (zero outside the
-// clip / image), optionally whole-tensor normalised first; columns 245..255 and frame slots t >= T are zero.
-// One CTA = one output row y of one frame slot: the 5 x 7 input rows it touches are staged in shared memory
-// (coalesced 352-byte row loads), then each warp emits whole 512-byte patch rows.
-__global__ void __launch_bounds__(256) frontend_im2col_kernel(const float* __restrict__ video, int B, int T, int Ta,
-                                                              const double* __restrict__ in_stats, double inv_count,
-                                                              __nv_bfloat16* __restrict__ col) {
-  __shared__ float tile[5][7][kImg];
+// Spatial patch matrix of the Conv3d front end: row (n, y, x) = frame slot n = b * Ta + t, output pixel (y, x) of 44 x 44;
+// column k = dy * 7 + dx < 49 holds video[b, t, 2y + dy - 3, 2x + dx - 3] (zero outside the image), optionally
+// whole-tensor normalised first; columns 49..63 and frame slots t >= T are zero.  The temporal extent of the kernel
+// (5 frames) is NOT unrolled into columns: the GEMM walks it as 5 taps that shift the A rows by whole frames
+// (44 * 44 rows), and Ta >= T + 2 keeps two all-zero frame slots between clips, which is the Conv3d's zero padding in
+// time.  One CTA = one output row y of one frame slot: the 7 input rows it touches are staged in shared memory.
+__global__ void __launch_bounds__(256) frontend_patch_kernel(const float* __restrict__ video, int B, int T, int Ta,
+                                                             const double* __restrict__ in_stats, double inv_count,
+                                                             __nv_bfloat16* __restrict__ col) {
+  __shared__ float tile[7][kImg];
   const int y = blockIdx.x % kF0;
   const int n = blockIdx.x / kF0;
   const int t = n % Ta, b = n / Ta;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __nv_bfloat16* out = col + (static_cast<size_t>(n) * kF0 + y) * kF0 * kFrontK;
   if (t >= T) {  // padding frame slot: all-zero patches
     for (int i = threadIdx.x; i < kF0 * kFrontK / 8; i += 256) reinterpret_cast<uint4*>(out)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -71,31 +72,26 @@ __global__ void __launch_bounds__(256) frontend_im2col_kernel(const float* __res
     mean = static_cast<float>(m);
     rstd = static_cast<float>(1.0 / sqrt((var > 0 ? var : 0) + 1e-5));
   }
-  for (int i = threadIdx.x; i < 5 * 7 * kImg; i += 256) {
-    const int xi = i % kImg, dy = (i / kImg) % 7, dt = i / (7 * kImg);
-    const int ti = t + dt - 2, yi = 2 * y + dy - 3;
+  for (int i = threadIdx.x; i < 7 * kImg; i += 256) {
+    const int xi = i % kImg, dy = i / kImg;
+    const int yi = 2 * y + dy - 3;
     float v = 0.f;  // zero padding of the (normalised) input
-    if (ti >= 0 && ti < T && yi >= 0 && yi < kImg) v = (__ldg(video + ((static_cast<size_t>(b) * T + ti) * kImg + yi) * kImg + xi) - mean) * rstd;
-    tile[dt][dy][xi] = v;
+    if (yi >= 0 && yi < kImg) v = (__ldg(video + ((static_cast<size_t>(b) * T + t) * kImg + yi) * kImg + xi) - mean) * rstd;
+    tile[dy][xi] = v;
   }
   __syncthreads();
-  int off[8], dxs[8];  // this lane's 8 patch columns: offset of (dt, dy) in the tile and dx
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int k = lane * 8 + i;
-    const int dx = k % 7, dy = (k / 7) % 7, dt = k / 49;
-    off[i] = k < 245 ? (dt * 7 + dy) * kImg : -1;
-    dxs[i] = dx - 3;
-  }
-  const float* flat = &tile[0][0][0];
-  for (int x = warp; x < kF0; x += 8) {
+  // work item = (x, 8-column chunk c8): 44 * 8 items, 16 bytes each, consecutive threads write consecutive chunks
+  for (int item = threadIdx.x; item < kF0 * (kFrontK / 8); item += 256) {
+    const int x = item >> 3, c8 = item & 7;
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int xi = 2 * x + dxs[i];
-      v[i] = (off[i] >= 0 && xi >= 0 && xi < kImg) ? flat[off[i] + xi] : 0.f;
+      const int k = c8 * 8 + i;
+      const int dy = k / 7, dx = k - dy * 7;
+      const int xi = 2 * x + dx - 3;
+      v[i] = (k < 49 && xi >= 0 && xi < kImg) ? tile[dy][xi] : 0.f;
     }
-    *reinterpret_cast<uint4*>(out + static_cast<size_t>(x) * kFrontK + lane * 8) =
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(x) * kFrontK + c8 * 8) =
         make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
 }
@@ -198,7 +194,7 @@ struct svt_video {
   svt_encoder* enc = nullptr;              // transformer body (positional conv + layers), transformer_only
   DevicePool pool;
   bool finalized = false;
-  ConvW front;                             // Conv3d as [64][256]
+  ConvW front;                             // Conv3d as [64][5][64]
   struct Block { ConvW c1, c2, ds; bool has_ds = false; };
   Block blocks[4][2];
   LinearW proj, post;
@@ -277,21 +273,24 @@ int finalize_video(svt_video* v) {
   const int D = v->cfg.embed_dim;
   v->pool.release();
   const std::string r = "feature_extractor_video.resnet.";
-  // ---- Conv3d front end (64, 1, 5, 7, 7) + BN3d + PReLU -> [64][256] (k = (dt*7 + dy)*7 + dx, zero padded)
+  // ---- Conv3d front end (64, 1, 5, 7, 7) + BN3d + PReLU -> [64][5 temporal taps][64] (k = dy*7 + dx, zero padded)
   {
     const HostTensor* w;
     SVT_TRY(need(v, r + "frontend3D.0.weight", {64, 1, 5, 7, 7}, &w));
     std::vector<float> scale, shift;
     SVT_TRY(bn_fold(v, r + "frontend3D.1.", 64, &scale, &shift));
-    std::vector<__nv_bfloat16> pw(static_cast<size_t>(64) * kFrontK, __float2bfloat16(0.f));
+    std::vector<__nv_bfloat16> pw(static_cast<size_t>(64) * kFrontT * kFrontK, __float2bfloat16(0.f));
     for (int co = 0; co < 64; ++co)
-      for (int k = 0; k < 245; ++k) pw[static_cast<size_t>(co) * kFrontK + k] = __float2bfloat16(w->v[static_cast<size_t>(co) * 245 + k] * scale[co]);
+      for (int dt = 0; dt < kFrontT; ++dt)
+        for (int k = 0; k < 49; ++k)
+          pw[(static_cast<size_t>(co) * kFrontT + dt) * kFrontK + k] =
+              __float2bfloat16(w->v[(static_cast<size_t>(co) * kFrontT + dt) * 49 + k] * scale[co]);
     SVT_TRY(upload(v->pool, pw, &v->front.w));
     SVT_TRY(upload(v->pool, shift, &v->front.bias));
     const HostTensor* a;
     SVT_TRY(need(v, r + "frontend3D.2.weight", {64}, &a));
     SVT_TRY(upload(v->pool, a->v, &v->front.alpha));
-    v->front.cin = kFrontK; v->front.cout = 64; v->front.taps = 1;
+    v->front.cin = kFrontK; v->front.cout = 64; v->front.taps = kFrontT;
   }
   // ---- ResNet-18 trunk (resnet.py:79-131): BasicBlock = conv1-bn1-prelu1-conv2-bn2 (+ downsample(x)) - prelu2
   int inpl = 64;
@@ -330,7 +329,8 @@ struct VideoPlan {
 };
 VideoPlan make_plan(const svt_video* v, int B, int T) {
   VideoPlan p{};
-  p.B = B; p.T = T; p.Ta = (T + 3) / 4 * 4; p.N = B * p.Ta;
+  // two all-zero frame slots after every clip = the temporal zero padding the front end's frame-shift taps read
+  p.B = B; p.T = T; p.Ta = (T + 2 + 3) / 4 * 4; p.N = B * p.Ta;
   const size_t N = p.N, D = v->cfg.embed_dim, F = v->cfg.ffn_size;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
@@ -368,6 +368,9 @@ int conv_gemm(const ConvW& w, const __nv_bfloat16* x, long long rows, int Hp, co
     g.n_taps = 9;
     for (int dy = 0; dy < 3; ++dy)
       for (int dx = 0; dx < 3; ++dx) g.tap_off[dy * 3 + dx] = (dy - 1) * Hp + (dx - 1);
+  } else if (w.taps == kFrontT) {  // front end: tap = frame shift, Hp = rows per frame
+    g.n_taps = kFrontT;
+    for (int dt = 0; dt < kFrontT; ++dt) g.tap_off[dt] = (dt - kFrontT / 2) * Hp;
   }
   return gemm_bf16_tc(g, s);
 }
@@ -399,10 +402,10 @@ int forward_video(svt_video* v, const float* video, int B, int T, void* ws, size
   // ---- Conv3d front end as patch matrix + GEMM (BN folded, PReLU epilogue)
   {
     const long long rows = static_cast<long long>(N) * kF0 * kF0;
-    frontend_im2col_kernel<<<N * kF0, 256, 0, s>>>(video, B, T, Ta, v->cfg.input_norm ? stats_in : nullptr,
-                                                             1.0 / (static_cast<double>(B) * T * kImg * kImg), col);
+    frontend_patch_kernel<<<N * kF0, 256, 0, s>>>(video, B, T, Ta, v->cfg.input_norm ? stats_in : nullptr,
+                                                  1.0 / (static_cast<double>(B) * T * kImg * kImg), col);
     SVT_POST_LAUNCH();
-    SVT_TRY(conv_gemm(v->front, col, rows, 0, nullptr, nullptr, true, f0, s));
+    SVT_TRY(conv_gemm(v->front, col, rows, kF0 * kF0, nullptr, nullptr, true, f0, s));
     maxpool_kernel<<<grid_for(static_cast<long long>(N) * 24 * 24 * 8, 256), 256, 0, s>>>(f0, N, buf[0]);
     SVT_POST_LAUNCH();
   }

@@ -253,12 +253,28 @@ class AVTranscriber:
         self.device = torch.device(device)
         self._decoder = AMTTranscriber.__new__(AMTTranscriber)
         self._decoder.hp = self.hp
+        self.concurrent_streams = True  # run the two encoders on two CUDA streams (their small-batch grids leave SMs idle)
+        self._side_stream = None
 
     @torch.no_grad()
     def logits(self, wav: torch.Tensor, video: torch.Tensor) -> torch.Tensor:
         """wav (B, L), video (B, 1, T, 88, 88) on CUDA -> frame logits (B, T_audio, 20)  (train_rca_av.py:38-49)."""
-        a = self.audio_lobe(wav)
+        if not self.concurrent_streams:
+            a = self.audio_lobe(wav)
+            v = self.video_lobe({"video": video, "audio": None})
+            return self.head(self.fusion(a, v))
+        # the two streams of the model are independent until the fusion: at the 4 clips per GPU of config 4 many of their
+        # GEMMs have fewer tiles than the GPU has SMs, so the other encoder's kernels fill the idle ones
+        main = torch.cuda.current_stream(wav.device)
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=wav.device)
+        side = self._side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            a = self.audio_lobe(wav)
         v = self.video_lobe({"video": video, "audio": None})
+        main.wait_stream(side)
+        a.record_stream(main)
         return self.head(self.fusion(a, v))
 
     def decode(self, logits: torch.Tensor) -> np.ndarray:

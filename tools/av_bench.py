@@ -47,8 +47,14 @@ def timeit(fn, n=5, warm=2):
 a = alobe(wav)
 v = vlobe({"video": video, "audio": None})
 t_all = timeit(lambda: tr.logits(wav, video))
+tr.concurrent_streams = False
+t_seq = timeit(lambda: tr.logits(wav, video))
+ref = tr.logits(wav, video)
+tr.concurrent_streams = True
+assert torch.equal(tr.logits(wav, video), ref)
 t_a = timeit(lambda: alobe(wav))
 t_v = timeit(lambda: vlobe({"video": video, "audio": None}))
 t_f = timeit(lambda: lin(fus(a, v)))
 print(f"AV pipeline B={B} x 10 s: {t_all:.2f} ms/step = {B * 10 / t_all * 1e3:.0f} audio-s/s per GPU "
+      f"with the two encoders on two streams, {t_seq:.2f} ms back to back "
       f"(audio lobe {t_a:.2f} ms, video lobe {t_v:.2f} ms, fusion + head {t_f:.2f} ms)")

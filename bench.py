@@ -142,6 +142,14 @@ def cpu_reference_throughput(n_timed: int, warmup: int, large: bool = True):
                       f"mean of {n_timed} passes after {warmup} warm-up", "s_per_clip": mean_t}
 
 
+def workload_config(B, world, T):
+    """The `config` object of both arms (BASELINE config 2; at N GPUs config 3's weak scaling)."""
+    return {"workload": f"wav2vec2-large AMT encoder+head (random init), {B} x 10-s 16 kHz clips per GPU per step "
+                        f"(BASELINE config 2; N=8 -> config 3's 512 clips), logits all-gathered over NCCL when N>1",
+            "global_batch": B * world, "frames_per_clip": T, "parallelism": f"dp{world}",
+            "l2": "inputs rotate over 4 x 41 MB buffers (> 126 MB L2) and each step streams > 3 GB of activations"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -153,7 +161,8 @@ def run_reference(args):
         "unit": "audio-sec/sec", "n_gpus": args.gpus, "steps": k, "warmup": max(1, min(args.warmup, 2)),
         "ms_per_step": cb["s_per_clip"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "wav2vec2-large AMT (random init) 10-s 16 kHz clips; CPU arm: bounded sample of 1 clip per step"},
+        "config": dict(workload_config(args.batch, args.gpus, 499),
+                       reference_sample="CPU arm: each step is a bounded sample of that workload, ONE 10-s clip (batch 1)"),
         "cpu_baseline": {k2: v for k2, v in cb.items() if k2 != "s_per_clip"},
         "e2e": {"value": cb["value"], "unit": "audio-sec/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -312,10 +321,7 @@ def run_ours(args):
             "metric": "audio-sec/sec (RTF^-1) wav2vec2-large AMT", "value": value, "unit": "audio-sec/sec",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"wav2vec2-large AMT encoder+head (random init), {B} x 10-s 16 kHz clips per GPU per step "
-                                   f"(BASELINE config 2; N=8 -> config 3's 512 clips), logits all-gathered over NCCL when N>1",
-                       "global_batch": B * world, "frames_per_clip": T, "parallelism": f"dp{world}",
-                       "l2": "inputs rotate over 4 x 41 MB buffers (> 126 MB L2) and each step streams > 3 GB of activations"},
+            "config": workload_config(B, world, T),
             "e2e": {"value": e2e_value, "unit": "audio-sec/sec", "h2d_bytes_per_step": B * L * 4,
                     "d2h_bytes_per_step": B * T * 20 * 4, "api": "svt_pipeline_submit / svt_pipeline_wait, depth 2 (pinned host wav -> H2D -> forward -> D2H pinned host logits, every step)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,

@@ -48,7 +48,8 @@ long long svt_debug_launch_count(void);
 
 /* process-wide tuning / test switches.  "attention_impl": 0 auto (default), 1 force the mma.sync kernel,
  * 2 force the tcgen05/TMEM kernel (head_dim 64 only).  "gemm_impl": 0 auto (CTA-pair cta_group::2 kernel when
- * N % 256 == 0), 1 force the one-CTA kernel.  "ln_fold": 1 (default) folds the two per-layer LayerNorms of pre-LN
+ * N % 256 == 0 and the problem has enough tiles, else the one-CTA kernel), 1 force the one-CTA kernel, 2 one-CTA kernel with
+ * 128-column tiles, 3 force the CTA-pair kernel.  "ln_fold": 1 (default) folds the two per-layer LayerNorms of pre-LN
  * (stable_layer_norm) transformer layers into the neighbouring GEMMs, 0 runs them as separate kernels. */
 int svt_set_option(const char* name, int value);
 

@@ -51,7 +51,8 @@ int svt_set_option(const char* name, int value) {
     return kOk;
   }
   if (n == "gemm_impl") {
-    if (value < 0 || value > 1) return fail(kInvalidArgument, "gemm_impl must be 0 (auto) or 1 (one-CTA kernel)");
+    if (value < 0 || value > 3)
+      return fail(kInvalidArgument, "gemm_impl must be 0 (auto), 1 (one-CTA kernel), 2 (one-CTA kernel, 128-column tiles) or 3 (CTA-pair kernel)");
     g_gemm_impl.store(value);
     return kOk;
   }

@@ -387,7 +387,19 @@ int gemm_bf16_tc(const GemmArgs& g, cudaStream_t stream) {
   }
   if (g.row_stats_out != nullptr && (g.mode != 0 || g.out_f32 == nullptr || g.N % 256 != 0 || g.ld_out != g.N))
     return fail(kInvalidArgument, "gemm: row statistics need mode 0, an fp32 output and N % 256 == 0 (= ld_out)");
-  if (get_option_gemm_impl() != 1 && gemm_pair_supported(g) && g.M >= 1024 && g.n_taps == 0) return gemm_bf16_tc_pair(g, stream);
+  // Kernel / tile choice.  The CTA-pair kernel (256 x 256 per SM pair) wins whenever there are enough tiles to keep the
+  // 74 pairs busy for a few waves; small row counts (a handful of clips) run on the one-CTA kernel with 128-column
+  // tiles, which cuts the problem into 4x as many work items.  A producer of LayerNorm statistics needs 256-column
+  // tiles (one 128-column slot per epilogue warp).
+  const int impl = get_option_gemm_impl();
+  const bool pair_ok = gemm_pair_supported(g) && g.n_taps == 0;
+  bool want_small = false;
+  if (g.mode == 0 && g.N % 128 == 0 && g.row_stats_out == nullptr) {
+    const long long units_pair = static_cast<long long>(ceil_div(g.M, 256)) * (g.N / 256 > 0 ? g.N / 256 : 1);
+    want_small = impl == 2 || (impl == 0 && units_pair < kSmallProblemPairUnits);
+  }
+  if (impl == 3 && pair_ok) return gemm_bf16_tc_pair(g, stream);
+  if (impl == 0 && pair_ok && !want_small && g.M >= 1024) return gemm_bf16_tc_pair(g, stream);
   KParams kp{};
   kp.mode = g.mode;
   kp.M = g.M;
@@ -449,7 +461,7 @@ int gemm_bf16_tc(const GemmArgs& g, cudaStream_t stream) {
     kp.clip_valid = g.clip_valid;
     kp.pad_left = g.pad_left;
   } else {
-    bn = (g.N % 256 == 0) ? 256 : (g.N % 128 == 0 ? 128 : 64);
+    bn = (g.N % 256 == 0 && !want_small) ? 256 : (g.N % 128 == 0 ? 128 : 64);
     if (g.N % bn != 0) return fail(kInvalidArgument, "gemm: N must be a multiple of 64");
     kp.m_tiles = ceil_div(g.M, BM);
     kp.n_tiles = g.N / bn;

@@ -7,6 +7,8 @@ namespace svt {
 
 enum GemmAct : int { kActNone = 0, kActGelu = 1, kActRelu = 2, kActPRelu = 3 };
 constexpr int kMaxGemmTaps = 9;
+// below this many 256 x 256 work items the one-CTA kernel with 128-column tiles is used (see gemm_bf16_tc)
+constexpr long long kSmallProblemPairUnits = 33;  // measured: profiles/r1_small_m_gemm_sweep.txt (tools/kernel_bench.py smallm)
 
 // C[row, n] = act( sum_k A[row, k] * W[n, k] + bias[n] ) (+ resid[row, n])
 //

@@ -185,3 +185,36 @@ def test_gemm_folded_layer_norm_chain(M, D, N, act, offset):
     print(f"folded LN M={M} D={D} N={N} offset={offset}: rel-L2 folded {e_fold:.3e} vs separate-LN {e_unf:.3e}")
     assert torch.isfinite(out.float()).all()
     assert e_fold < 1e-2 and e_fold < 3 * e_unf + 1e-3
+
+
+@pytest.mark.parametrize("M,N,K,act,resid", [(2016, 1024, 4096, 0, True), (2016, 3072, 1024, 0, False), (500, 4096, 1024, 1, False),
+                                            (1000, 1024, 1024, 0, True)])
+def test_gemm_kernel_choices_agree(M, N, K, act, resid):
+    """Option "gemm_impl": the CTA-pair kernel, the one-CTA kernel with 256-column tiles and with 128-column tiles (the
+    small-problem path) compute the same thing; 0 = automatic choice."""
+    from gpu_util import rel_l2
+    from svt_speechbrain_b200._lib import check, current_stream_ptr, lib, ptr
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    r0 = torch.randn(M, N, device="cuda", generator=g) if resid else None
+    ref = _ref(a, w, bias, r0, act)
+    outs = {}
+    try:
+        for impl in (0, 1, 2, 3):
+            check(lib().svt_set_option(b"gemm_impl", impl))
+            if resid:
+                o = r0.clone()
+                check(lib().svt_op_gemm(ptr(a), K, K, ptr(w), ptr(bias), ptr(o), ptr(o), None, M, N, K, N, act, current_stream_ptr()))
+            else:
+                o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+                check(lib().svt_op_gemm(ptr(a), K, K, ptr(w), ptr(bias), None, None, ptr(o), M, N, K, N, act, current_stream_ptr()))
+            torch.cuda.synchronize()
+            outs[impl] = o.float()
+    finally:
+        lib().svt_set_option(b"gemm_impl", 0)
+    for impl, o in outs.items():
+        assert rel_l2(o, ref) < 4e-3, impl
+    # same k-order of the accumulation in every tiling: the variants agree exactly
+    assert torch.equal(outs[1], outs[2]) and torch.equal(outs[1], outs[3]) and torch.equal(outs[0], outs[1])

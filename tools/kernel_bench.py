@@ -99,6 +99,16 @@ def main():
             gemm("qkv shape K=256", M, 3072, 256, act=0, out=out)
             gemm("qkv shape gelu K=256", M, 3072, 256, act=1, out=out)
         gemm("proj 512->1024 (fp32 out)", M, 1024, 512, f32=True, out=out)
+    if "smallm" in which:
+        # kernel / tile choice for small row counts: CTA-pair (3) vs one-CTA 256-column (1) vs one-CTA 128-column tiles (2)
+        for clips in (1, 2, 4, 8, 12, 16, 24, 32):
+            m = clips * Ta
+            for nm, (N_, K_, act_, res_) in {"qkv": (3072, 1024, 0, False), "out": (1024, 1024, 0, True),
+                                             "ffn1": (4096, 1024, 1, False), "ffn2": (1024, 4096, 0, True)}.items():
+                for impl in (3, 1, 2):
+                    check(lib().svt_set_option(b"gemm_impl", impl))
+                    gemm(f"{nm} clips={clips} impl={impl}", m, N_, K_, act=act_, resid=res_, out=out)
+        check(lib().svt_set_option(b"gemm_impl", 0))
     if "conv" in which:
         gemm("conv1 k3s2 (implicit)", 1024000, 512, 1536, k_inner=512, row_stride=1024, out=out)
         gemm("conv2 k3s2 (implicit)", 512000, 512, 1536, k_inner=512, row_stride=1024, out=out)

@@ -591,7 +591,9 @@ static int forward_impl(svt_encoder* e, const float* wav, int B, int L, void* ws
   uint8_t* base = static_cast<uint8_t*>(ws);
   double* stats_in = reinterpret_cast<double*>(base + p.off_stats);
   double* stats_out = stats_in + 2 * static_cast<size_t>(B);
-  const int stats_stride = e->norm_per_clip ? 2 : 0;
+  // a single clip is its own normalisation scope either way: route it through the per-clip statistics so that its
+  // result is bit-identical to the same clip inside a larger per-clip batch
+  const int stats_stride = (e->norm_per_clip || B == 1) ? 2 : 0;
   double* chan = reinterpret_cast<double*>(base + p.off_chan);
   __nv_bfloat16* bufA = reinterpret_cast<__nv_bfloat16*>(base + p.off_bufA);
   __nv_bfloat16* bufB = reinterpret_cast<__nv_bfloat16*>(base + p.off_bufB);

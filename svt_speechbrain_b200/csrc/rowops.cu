@@ -556,7 +556,7 @@ int tensor_stats(const float* x, size_t n, double* stats, cudaStream_t stream) {
 
 int tensor_stats_per_clip(const float* x, int clips, size_t n_per_clip, double* stats, cudaStream_t stream) {
   SVT_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(double) * clips, stream));
-  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || n_per_clip % 4 != 0)
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (clips > 1 && n_per_clip % 4 != 0))
     return fail(kInvalidArgument, "per-clip statistics need 16-byte aligned clips (n_samples % 4 == 0)");
   // CTAs per clip depend on the clip length only, never on the batch: a clip's partial sums (and so its statistics and
   // everything downstream) are the same whichever batch or rank it is processed in

@@ -132,16 +132,25 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
   float ps[8], pss[8];  // producer side: per-lane partial row statistics over this warp's columns
 #pragma unroll
   for (int i = 0; i < 8; ++i) ps[i] = pss[i] = 0.f;
-  // the TMEM read of chunk c + 1 is issued before the math of chunk c and stays in flight under it
+  // The TMEM read of chunk c + 1 is issued before the math of chunk c and stays in flight under it.  The chunk loop is
+  // unrolled by two over two register arrays that swap roles, so no accumulator is ever copied between registers.
   const uint32_t tmem_row = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(half * kColsPerWarp);
-  uint32_t rn[32];
-  tmem_ld32(tmem_row, rn);
-#pragma unroll 1
-  for (int c = 0; c < kColsPerWarp; c += 32) {
+
+  // one 32-column chunk whose accumulators are arriving in `acc`; `nxt` receives the following chunk's TMEM read
+  auto chunk_cols = [&](int c, int* col, int* nv) {
     const int col_in_tile = half * kColsPerWarp + c;
-    const int col = col0 + col_in_tile;
-    const int nv = n_valid - col_in_tile;  // valid columns of this 32-wide chunk
-    if (f32_path) {
+    *col = col0 + col_in_tile;
+    *nv = n_valid - col_in_tile;  // valid columns of this 32-wide chunk
+  };
+  if (f32_path) {
+    // fp32 / residual outputs: HBM-bound epilogues; one register array, copied once per chunk
+    uint32_t rn[32];
+    tmem_ld32(tmem_row, rn);
+#pragma unroll 1
+    for (int c = 0; c < kColsPerWarp; c += 32) {
+      int col, nv;
+      chunk_cols(c, &col, &nv);
+      uint32_t acc[32];
       // residual + bias of this chunk in the coalesced mapping (lane = 4 columns of rows 4i + lane / 8), all loads
       // issued before the TMEM read so their latency overlaps it (resid may alias out_f32: loads come first)
       float4 rs[8];
@@ -173,14 +182,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
                                                      static_cast<size_t>(col + 4 * c4));
         }
       }
-      uint32_t r[32];
       tmem_ld_wait_regs(rn);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = rn[j];
+      for (int j = 0; j < 32; ++j) acc[j] = rn[j];
       if (c + 32 < kColsPerWarp) tmem_ld32(tmem_row + c + 32, rn);
 #pragma unroll
       for (int q = 0; q < 8; ++q)
-        epi_sts128(stage_addr + lane * 128 + ((q ^ (lane & 7)) << 4), r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        epi_sts128(stage_addr + lane * 128 + ((q ^ (lane & 7)) << 4), acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
       __syncwarp();
       uint4 raw[8];
 #pragma unroll
@@ -221,12 +229,18 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
         }
       }
       __syncwarp();
-    } else {
-      tmem_ld_wait_regs(rn);
+    }
+  } else {
+    // bf16-only outputs (QKV, FFN-1 with GELU: issue-bound): the loop is unrolled by two over two register arrays
+    // that swap roles, so no accumulator is ever copied between registers
+    auto chunk = [&](uint32_t (&acc)[32], uint32_t (&nxt)[32], int c) {
+      int col, nv;
+      chunk_cols(c, &col, &nv);
+      tmem_ld_wait_regs(acc);
+      if (c + 32 < kColsPerWarp) tmem_ld32(tmem_row + c + 32, nxt);
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rn[j]);
-      if (c + 32 < kColsPerWarp) tmem_ld32(tmem_row + c + 32, rn);
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
       if (ln) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -273,6 +287,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
                                     static_cast<size_t>(col + 8 * sl)) = o[i];
       }
       __syncwarp();
+    };
+    uint32_t ra[32], rb2[32];
+    tmem_ld32(tmem_row, ra);
+#pragma unroll 1
+    for (int c = 0; c < kColsPerWarp; c += 64) {
+      chunk(ra, rb2, c);
+      if (c + 32 < kColsPerWarp) chunk(rb2, ra, c + 32);
     }
   }
   if constexpr (BN == 256) {

@@ -117,6 +117,27 @@ class AMTTranscriber:
             eng.set_norm_per_clip(False)
         return lg
 
+    @torch.no_grad()
+    def _clip_logits(self, clips: Sequence[torch.Tensor], batch_clips: int, per_clip_norm: bool) -> List[torch.Tensor]:
+        """Frame logits (T_i, 20) of 1-D clips, in order.  Runs of consecutive equal-length clips go through the encoder
+        as one batch of at most `batch_clips`; with per_clip_norm every clip is normalised on its own (the reference's
+        batch-size-1 evaluation), which needs 16-byte aligned clips inside a batch -- otherwise one call per clip."""
+        out: List[torch.Tensor] = []
+        i = 0
+        while i < len(clips):
+            j = i
+            L = clips[i].numel()
+            while j < len(clips) and j - i < batch_clips and clips[j].numel() == L:
+                j += 1
+            batch = torch.stack(list(clips[i:j]))
+            if per_clip_norm and j - i > 1 and L % 4 != 0:
+                lg = torch.cat([self.logits(c.unsqueeze(0)) for c in batch], dim=0)
+            else:  # a single clip is its own normalisation scope either way
+                lg = self.logits(batch, per_clip_norm=per_clip_norm and j - i > 1)
+            out.extend(lg[k] for k in range(lg.shape[0]))
+            i = j
+        return out
+
     def frame_info(self, logits: torch.Tensor):
         """(n_frames, 20) CUDA logits -> host arrays (p_on f32, p_off f32, octave i32, pitch_class i32).
         argmax runs on the device (first max wins); the two sigmoids are taken on the HOST with torch so the
@@ -149,20 +170,7 @@ class AMTTranscriber:
         utterance at a time) with the per-clip normalisation scope of the encoder, still in batched calls."""
         wav = wav.to(self.device, torch.float32).reshape(-1)
         spans = split_song(wav.numel(), self.hp, dur)
-        pieces: List[torch.Tensor] = []
-        i = 0
-        while i < len(spans):
-            j = i
-            L = spans[i][1] - spans[i][0]
-            while j < len(spans) and j - i < batch_clips and spans[j][1] - spans[j][0] == L:
-                j += 1
-            clips = torch.stack([wav[a:b] for a, b in spans[i:j]])
-            if per_clip_norm and j - i > 1 and L % 4 != 0:  # unaligned clip length: one call per utterance
-                lg = torch.cat([self.logits(c.unsqueeze(0)) for c in clips], dim=0)
-            else:  # a single clip is its own normalisation scope either way
-                lg = self.logits(clips, per_clip_norm=per_clip_norm and j - i > 1)
-            pieces.extend(lg[k] for k in range(lg.shape[0]))
-            i = j
+        pieces = self._clip_logits([wav[a:b] for a, b in spans], batch_clips, per_clip_norm)
         return self.decode(torch.cat(pieces, dim=0))
 
     @torch.no_grad()
@@ -186,21 +194,7 @@ class AMTTranscriber:
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         lo, hi = shard_range(len(windows), rank, world)
-        mine = windows[lo:hi]
-        local: List[torch.Tensor] = []
-        i = 0
-        while i < len(mine):
-            j = i
-            L = mine[i][1] - mine[i][0]
-            while j < len(mine) and j - i < batch_clips and mine[j][1] - mine[j][0] == L:
-                j += 1
-            clips = torch.stack([wav[a:b] for a, b in mine[i:j]])
-            if per_clip_norm and j - i > 1 and L % 4 != 0:
-                lg = torch.cat([self.logits(c.unsqueeze(0)) for c in clips], dim=0)
-            else:
-                lg = self.logits(clips, per_clip_norm=per_clip_norm and j - i > 1)
-            local.extend(lg[k] for k in range(lg.shape[0]))
-            i = j
+        local = self._clip_logits([wav[a:b] for a, b in windows[lo:hi]], batch_clips, per_clip_norm)
         pieces = gather_ragged(local, len(windows), group) if world > 1 else local
         plan = stitch_plan(windows)
         return torch.cat([p[a:b] for p, (a, b) in zip(pieces, plan)], dim=0)
@@ -218,21 +212,9 @@ class AMTTranscriber:
         for si, w in enumerate(songs):
             for ui, (a, b) in enumerate(split_song(w.numel(), hp, dur)):
                 jobs.append((b - a, si, ui, a, b))
-        out = {}
-        jobs.sort(key=lambda t: (t[0], t[1], t[2]))
-        i = 0
-        while i < len(jobs):
-            j = i
-            while j < len(jobs) and j - i < batch_clips and jobs[j][0] == jobs[i][0]:
-                j += 1
-            clips = torch.stack([songs[si][a:b] for _, si, _, a, b in jobs[i:j]])
-            if per_clip_norm and jobs[i][0] % 4 != 0 and j - i > 1:
-                lg = torch.cat([self.logits(c.unsqueeze(0)) for c in clips], dim=0)
-            else:
-                lg = self.logits(clips, per_clip_norm=per_clip_norm and j - i > 1)
-            for k, (_, si, ui, _, _) in enumerate(jobs[i:j]):
-                out[(si, ui)] = lg[k]
-            i = j
+        jobs.sort(key=lambda t: (t[0], t[1], t[2]))  # equal lengths become neighbours
+        lgs = self._clip_logits([songs[si][a:b] for _, si, _, a, b in jobs], batch_clips, per_clip_norm)
+        out = {(si, ui): lg for (_, si, ui, _, _), lg in zip(jobs, lgs)}
         results = []
         for si, w in enumerate(songs):
             n_utt = len(split_song(w.numel(), hp, dur))

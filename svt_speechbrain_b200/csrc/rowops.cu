@@ -272,12 +272,14 @@ groupnorm_gelu_kernel(__nv_bfloat16* __restrict__ x, const double* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------ output norm + head
+constexpr int head_rows(int nv) { return nv > 8 ? 2 : 4; }  // frames per warp and pass (register budget)
 template <int NV>
 __global__ void __launch_bounds__(256)
 head_kernel(const float* __restrict__ x, int clips, int clip_rows, int T, const double* __restrict__ stats, float eps,
             const float* __restrict__ w, const float* __restrict__ b, int n_out, float* __restrict__ feats,
             float* __restrict__ logits, int w_in_smem, int stats_stride) {
   constexpr int D = NV * 128;
+  constexpr int kHeadRows = head_rows(NV);
   extern __shared__ __align__(16) float sw[];
   if (w != nullptr && w_in_smem)
     for (int i = threadIdx.x; i < n_out * D; i += blockDim.x) sw[i] = w[i];
@@ -287,33 +289,60 @@ head_kernel(const float* __restrict__ x, int clips, int clip_rows, int T, const 
   const float* wp = w_in_smem ? sw : w;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = clips * T;
-  for (int fr = blockIdx.x * 8 + warp; fr < total; fr += gridDim.x * 8) {
-    const int clip = fr / T, t = fr % T;
-    if (stats != nullptr && stats_stride > 0)
-      mean_rstd_from_stats(stats + static_cast<size_t>(clip) * stats_stride, static_cast<double>(T) * D, eps, mean, rstd);
-    const float* xr = x + (static_cast<size_t>(clip) * clip_rows + t) * D;
-    float4 v[NV];
+  // kHeadRows frames per warp and pass: every weight vector read from shared memory feeds kHeadRows dot products (the
+  // kernel is bound by those reads, not by HBM)
+  int cached_clip = -1;
+  for (int fr0 = (blockIdx.x * 8 + warp) * kHeadRows; fr0 < total; fr0 += gridDim.x * 8 * kHeadRows) {
+    float4 v[kHeadRows][NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
-      v[i].x = (v[i].x - mean) * rstd; v[i].y = (v[i].y - mean) * rstd;
-      v[i].z = (v[i].z - mean) * rstd; v[i].w = (v[i].w - mean) * rstd;
-      if (feats != nullptr) *reinterpret_cast<float4*>(feats + static_cast<size_t>(fr) * D + (i * 32 + lane) * 4) = v[i];
+    for (int r = 0; r < kHeadRows; ++r) {
+      const int fr = fr0 + r;
+      if (fr < total) {
+        const int clip = fr / T, t = fr % T;
+        if (stats != nullptr && stats_stride > 0 && clip != cached_clip) {
+          mean_rstd_from_stats(stats + static_cast<size_t>(clip) * stats_stride, static_cast<double>(T) * D, eps, mean, rstd);
+          cached_clip = clip;
+        }
+        const float* xr = x + (static_cast<size_t>(clip) * clip_rows + t) * D;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          float4 a = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+          a.x = (a.x - mean) * rstd; a.y = (a.y - mean) * rstd; a.z = (a.z - mean) * rstd; a.w = (a.w - mean) * rstd;
+          if (feats != nullptr) *reinterpret_cast<float4*>(feats + static_cast<size_t>(fr) * D + (i * 32 + lane) * 4) = a;
+          v[r][i] = a;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     if (logits != nullptr) {
-      float mine = 0.f;
+      float mine[kHeadRows];
+#pragma unroll
+      for (int r = 0; r < kHeadRows; ++r) mine[r] = 0.f;
       for (int n = 0; n < n_out; ++n) {
-        float acc = 0.f;
+        float acc[kHeadRows];
+#pragma unroll
+        for (int r = 0; r < kHeadRows; ++r) acc[r] = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           const float4 ww = *reinterpret_cast<const float4*>(wp + static_cast<size_t>(n) * D + (i * 32 + lane) * 4);
-          acc = fmaf(v[i].x, ww.x, acc); acc = fmaf(v[i].y, ww.y, acc);
-          acc = fmaf(v[i].z, ww.z, acc); acc = fmaf(v[i].w, ww.w, acc);
+#pragma unroll
+          for (int r = 0; r < kHeadRows; ++r) {
+            acc[r] = fmaf(v[r][i].x, ww.x, acc[r]); acc[r] = fmaf(v[r][i].y, ww.y, acc[r]);
+            acc[r] = fmaf(v[r][i].z, ww.z, acc[r]); acc[r] = fmaf(v[r][i].w, ww.w, acc[r]);
+          }
         }
-        acc = warp_sum(acc);
-        if (lane == n) mine = acc + (b != nullptr ? b[n] : 0.f);
+        const float bn = b != nullptr ? b[n] : 0.f;
+#pragma unroll
+        for (int r = 0; r < kHeadRows; ++r) {
+          const float tot = warp_sum(acc[r]);
+          if (lane == n) mine[r] = tot + bn;
+        }
       }
-      if (lane < n_out) logits[static_cast<size_t>(fr) * n_out + lane] = mine;
+#pragma unroll
+      for (int r = 0; r < kHeadRows; ++r)
+        if (lane < n_out && fr0 + r < total) logits[static_cast<size_t>(fr0 + r) * n_out + lane] = mine[r];
     }
   }
 }
@@ -609,7 +638,7 @@ int head_forward(const HeadArgs& a, cudaStream_t stream) {
       SVT_CUDA(cudaFuncSetAttribute(head_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       attr_set = true;
     }
-    int grid = ceil_div(a.clips * a.T, 8);
+    int grid = ceil_div(a.clips * a.T, 8 * head_rows(NV));
     if (grid > num_sms()) grid = num_sms();
     head_kernel<NV><<<grid, 256, smem, stream>>>(a.x, a.clips, a.clip_rows, a.T, a.stats, a.eps, a.w, a.b, a.n_out,
                                                  a.feats, a.logits, w_in_smem, a.stats_stride);

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(kAttnThreads, (DH == 64) ? 2 : 1)
 attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                  const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ o, int ldq, int ldk, int ldv, int ldo,
                  int Tq, int Tk, int q_clip_rows, int k_clip_rows, const float* __restrict__ rel_tab,
-                 const float* __restrict__ gate, int heads) {
+                 const float* __restrict__ gate, int heads, int rel_stride) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + kBQ * DH * 2;
@@ -146,7 +146,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
     if (rel_tab != nullptr) {
       // WavLM: + gate[row] * table[key - row] (Toeplitz bias, one 2 Tk - 1 entry table per head)
       const int ra = q0 + warp * 16 + (lane >> 2), rb = ra + 8;
-      const float* tb = rel_tab + static_cast<size_t>(head) * (2 * Tk - 1) + (Tk - 1);
+      const float* tb = rel_tab + static_cast<size_t>(head) * rel_stride + (Tk - 1);
       const float* gp = gate + static_cast<size_t>(clip) * q_clip_rows * heads + head;
       const float ga = ra < Tq ? gp[static_cast<size_t>(ra) * heads] : 0.f;
       const float gb = rb < Tq ? gp[static_cast<size_t>(rb) * heads] : 0.f;
@@ -256,7 +256,7 @@ int launch_attention(const AttentionArgs& a, cudaStream_t stream) {
   }
   dim3 grid(ceil_div(a.Tq, kBQ), a.heads, a.clips);
   attention_kernel<DH><<<grid, kAttnThreads, smem, stream>>>(a.q, a.k, a.v, a.o, a.ldq, a.ldk, a.ldv, a.ldo, a.Tq, a.Tk,
-                                                             a.q_clip_rows, a.k_clip_rows, a.rel_tab, a.gate, a.heads);
+                                                             a.q_clip_rows, a.k_clip_rows, a.rel_tab, a.gate, a.heads, a.rel_tab_stride);
   SVT_POST_LAUNCH();
   return kOk;
 }
@@ -268,7 +268,9 @@ int attention_bf16(const AttentionArgs& a, cudaStream_t stream) {
   if ((a.ldq | a.ldk | a.ldv) % 8 != 0 || a.ldo % 2 != 0) return fail(kInvalidArgument, "attention: misaligned leading dims");
   const int impl = get_option_attention_impl();
   if (a.rel_tab != nullptr) {
-    if (a.gate == nullptr || a.Tq != a.Tk) return fail(kInvalidArgument, "attention: relative position bias needs gates and Tq == Tk");
+    if (a.gate == nullptr || a.Tq != a.Tk || a.rel_tab_stride < 2 * a.Tk - 1 + 128)
+      return fail(kInvalidArgument, "attention: relative position bias needs gates, Tq == Tk and a padded table");
+    if (a.head_dim == 64 && impl != 1 && a.ldo % 8 == 0) return attention_bf16_tc(a, stream);
     if (a.head_dim == 64) return launch_attention<64>(a, stream);
     if (a.head_dim == 128) return launch_attention<128>(a, stream);
     return fail(kUnsupported, "attention: head_dim must be 64 or 128");

@@ -175,7 +175,8 @@ __device__ __forceinline__ float row_probs(const float (&sc)[kBlockK], uint32_t 
 __global__ void __launch_bounds__(kThreadsTc, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, int ldo, int Tq, int Tk,
-                    int q_clip_rows, int heads, int n_qpairs, int n_items, long long* __restrict__ trace) {
+                    int q_clip_rows, int heads, int n_qpairs, int n_items, long long* __restrict__ trace,
+                    const float* __restrict__ rel_tab, int rel_stride, const float* __restrict__ gate) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                // 2 buffers x 2 tiles
@@ -389,6 +390,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++li) {
       float m_run = 0.f;  // log2 domain
       float l_run = 0.f;
+      // WavLM gated relative position bias: score(i, j) += gate[i] * table[j - i]; this thread's row i is fixed per item
+      float bias_gate = 0.f;
+      const float* bias_row = nullptr;
+      if (rel_tab != nullptr) {
+        const int head = (item / n_qpairs) % heads;
+        const int clip = item / (n_qpairs * heads);
+        int qi = (item % n_qpairs) * 2 * kTileQ + t * kTileQ + row;
+        if (qi > Tq - 1) qi = Tq - 1;  // padding rows of the last tile: any in-range address, results are discarded
+        bias_gate = gate[(static_cast<size_t>(clip) * q_clip_rows + qi) * heads + head];
+        bias_row = rel_tab + static_cast<size_t>(head) * rel_stride + (Tk - 1 - qi);
+      }
       for (int j = 0; j < nb; ++j) {
         const int g = li * nb + j;
         if (rec) stamp(t);
@@ -412,6 +424,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[t]);
         if (rec) stamp(t);
+        if (bias_row != nullptr) {
+          // the table is padded with kBlockK zeros per head, so the key tail of the last block reads in range
+          const float* tb = bias_row + j * kBlockK;
+#pragma unroll
+          for (int c = 0; c < kBlockK; ++c) sc[c] = fmaf(bias_gate, __ldg(tb + c), sc[c]);
+        }
         if (j == nb - 1 && tail_valid < kBlockK) mask_tail(sc, tail_valid);
         const float m_blk = row_max(sc) * kLog2e;
         if (j == 0) {
@@ -499,7 +517,8 @@ int attention_bf16_tc(const AttentionArgs& a, cudaStream_t stream) {
   const int n_items = n_qpairs * a.heads * a.clips;
   const int grid = n_items < num_sms() ? n_items : num_sms();
   attention_tc_kernel<<<grid, kThreadsTc, kSmemTc, stream>>>(tmQ, tmK, tmV, a.o, a.ldo, a.Tq, a.Tk, a.q_clip_rows, a.heads,
-                                                            n_qpairs, n_items, attention_trace_buffer());
+                                                            n_qpairs, n_items, attention_trace_buffer(), a.rel_tab, a.rel_tab_stride,
+                                                            a.gate);
   SVT_POST_LAUNCH();
   return kOk;
 }

@@ -424,6 +424,8 @@ int linear(const __nv_bfloat16* a, int M, const LinearW& w, const float* resid, 
 // hb (its bf16 copy), rows = clip * Ta + t.  Out: *final_x points at the fp32 rows to normalise / hand to the head;
 // if stats_out != nullptr it receives sum / sum-of-squares of those rows over t < T (whole-tensor output norm).
 namespace svt {
+// row stride of the WavLM position-bias table of a T-frame clip: 2T - 1 entries + one key block of zeros, 16-byte multiple
+static int rel_tab_stride(int T) { return (2 * T - 1 + 128 + 3) / 4 * 4; }
 size_t transformer_rowstats_bytes(const svt_encoder* e, size_t M) {
   // two [M][D / 128][2] fp32 buffers; 0 when the LayerNorm fold does not apply (post-LN model or unsupported width)
   const int D = e->cfg.hidden_size;
@@ -496,11 +498,12 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
   if (c.rel_pos_buckets > 0) {
     auto it = e->rel_tabs.find(T);
     if (it == e->rel_tabs.end()) {
-      std::vector<float> tab(static_cast<size_t>(H) * (2 * T - 1));
+      const int stride = rel_tab_stride(T);
+      std::vector<float> tab(static_cast<size_t>(H) * stride, 0.f);  // zero tail: the kernels read whole key blocks
       for (int d = -(T - 1); d <= T - 1; ++d) {
         const int bucket = wavlm_relative_bucket(d, c.rel_pos_buckets, c.rel_pos_max_distance);
         for (int hh = 0; hh < H; ++hh)
-          tab[static_cast<size_t>(hh) * (2 * T - 1) + d + T - 1] = e->rel_embed[static_cast<size_t>(bucket) * H + hh];
+          tab[static_cast<size_t>(hh) * stride + d + T - 1] = e->rel_embed[static_cast<size_t>(bucket) * H + hh];
       }
       float* dev = nullptr;
       SVT_TRY(const_cast<svt_encoder*>(e)->pool.alloc_t<float>(tab.size(), &dev));
@@ -517,7 +520,7 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
     a.Tq = T; a.Tk = T; a.q_clip_rows = Ta; a.k_clip_rows = Ta; a.clips = B; a.heads = H; a.head_dim = dh;
     if (rel_tab != nullptr) {
       SVT_TRY(wavlm_gate(x_rows, M, H, Lw.gate_w2, Lw.gate_b2, Lw.gate_const, tb.gate, s));
-      a.rel_tab = rel_tab; a.gate = tb.gate;
+      a.rel_tab = rel_tab; a.rel_tab_stride = rel_tab_stride(T); a.gate = tb.gate;
     }
     return attention_bf16(a, s);
   };

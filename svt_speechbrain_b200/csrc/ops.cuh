@@ -15,9 +15,11 @@ struct AttentionArgs {
   int q_clip_rows = 0, k_clip_rows = 0; // allocated rows per clip
   int clips = 0, heads = 0, head_dim = 0;
   // WavLM gated relative position bias (HF modeling_wavlm.py, WavLMAttention.forward): the score of (query i, key j) gets
-  // gate[(clip * q_clip_rows + i) * heads + head] * rel_tab[head * (2 * Tk - 1) + (j - i) + Tk - 1] added before the
-  // softmax.  Self-attention only (Tq == Tk); served by the mma.sync kernel.
+  // gate[(clip * q_clip_rows + i) * heads + head] * rel_tab[head * rel_tab_stride + (j - i) + Tk - 1] added before the
+  // softmax.  Self-attention only (Tq == Tk); rel_tab_stride >= 2 * Tk - 1 + 128 with zeros after the 2 * Tk - 1 entries
+  // (the tcgen05 kernel reads whole 128-key blocks).
   const float* rel_tab = nullptr;
+  int rel_tab_stride = 0;
   const float* gate = nullptr;
 };
 int attention_bf16(const AttentionArgs& a, cudaStream_t stream);       // dispatcher

@@ -385,3 +385,27 @@ def test_long_form_windows_stitched_vs_oracle():
                          for (s, e), (lo, hi) in zip(windows, stitch_plan(windows))])
     assert got.shape == ref.shape == ((wav.numel() - 400) // 320 + 1, 20)
     _check_logits(got, ref.numpy(), "long-form stitched logits")
+
+
+def test_wavlm_position_bias_in_both_attention_kernels():
+    """WavLM's gated relative position bias runs in the tcgen05 attention kernel (default) and in the mma.sync kernel
+    (attention_impl = 1): both match the reference golden (249 frames: two key blocks, the second one partial)."""
+    from oracle import make_golden as mg
+    from oracle import wav2vec2_oracle as wo
+    import svt_speechbrain_b200 as svt
+    from svt_speechbrain_b200._lib import check, lib
+
+    g = np.load(os.path.join(GOLD, "wavlm_base_5s.npz"))
+    cfg = wo.W2V2Config.wavlm_base()
+    lobe, lin, sd, head = _build(cfg)
+    tr = svt.AMTTranscriber(lobe, lin)
+    wav = mg.synth_wav(int(g["B"]), int(g["L"]), seed=int(g["wav_seed"])).cuda()
+    outs = {}
+    try:
+        for impl in (1, 2):
+            check(lib().svt_set_option(b"attention_impl", impl))
+            outs[impl] = tr.logits(wav).cpu()
+            _check_logits(outs[impl], g["logits"], f"wavlm attention_impl={impl}")
+    finally:
+        lib().svt_set_option(b"attention_impl", 0)
+    assert float((outs[1] - outs[2]).abs().max()) < 5e-2

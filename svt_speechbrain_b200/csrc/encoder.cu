@@ -328,6 +328,30 @@ int svt::encoder_finalize(svt_encoder* e) {
       SVT_CUDA(cudaMemcpy(L.gate_w2, w2.data(), sizeof(float) * w2.size(), cudaMemcpyHostToDevice));
       SVT_CUDA(cudaMemcpy(L.gate_b2, b2.data(), sizeof(float) * 2, cudaMemcpyHostToDevice));
       SVT_CUDA(cudaMemcpy(L.gate_const, gc->dev, sizeof(float) * H, cudaMemcpyDeviceToDevice));
+      if (transformer_rowstats_bytes(e, 1) > 0) {
+        // the same gate on un-normalised rows (LayerNorm fold): per head w2 o gamma_h, its row sums, w2 . beta_h + b2
+        std::vector<float> gam(D), bet(D), w2g(static_cast<size_t>(H) * 2 * dh), cg(2 * H, 0.f), dg(2 * H);
+        SVT_CUDA(cudaMemcpy(gam.data(), L.ln1.g, sizeof(float) * D, cudaMemcpyDeviceToHost));
+        SVT_CUDA(cudaMemcpy(bet.data(), L.ln1.b, sizeof(float) * D, cudaMemcpyDeviceToHost));
+        for (int hh = 0; hh < H; ++hh)
+          for (int r = 0; r < 2; ++r) {
+            double csum = 0.0, dsum = b2[r];
+            for (int k = 0; k < dh; ++k) {
+              const float wg = w2[r * dh + k] * gam[hh * dh + k];
+              w2g[(static_cast<size_t>(hh) * 2 + r) * dh + k] = wg;
+              csum += wg;
+              dsum += static_cast<double>(w2[r * dh + k]) * bet[hh * dh + k];
+            }
+            cg[2 * hh + r] = static_cast<float>(csum);
+            dg[2 * hh + r] = static_cast<float>(dsum);
+          }
+        SVT_TRY(pool.alloc_t<float>(w2g.size(), &L.gate_w2g));
+        SVT_TRY(pool.alloc_t<float>(cg.size(), &L.gate_cg));
+        SVT_TRY(pool.alloc_t<float>(dg.size(), &L.gate_dg));
+        SVT_CUDA(cudaMemcpy(L.gate_w2g, w2g.data(), sizeof(float) * w2g.size(), cudaMemcpyHostToDevice));
+        SVT_CUDA(cudaMemcpy(L.gate_cg, cg.data(), sizeof(float) * cg.size(), cudaMemcpyHostToDevice));
+        SVT_CUDA(cudaMemcpy(L.gate_dg, dg.data(), sizeof(float) * dg.size(), cudaMemcpyHostToDevice));
+      }
     }
     if (transformer_rowstats_bytes(e, 1) > 0) {
       // second copies of the two Linears that read a LayerNorm, with the norm folded in
@@ -513,13 +537,16 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
     }
     rel_tab = it->second;
   }
-  auto attend = [&](const svt_encoder::Layer& Lw, const __nv_bfloat16* x_rows) {
+  auto attend = [&](const svt_encoder::Layer& Lw, const __nv_bfloat16* x_rows, const float* x_stats = nullptr) {
     AttentionArgs a;
     a.q = qkv; a.k = qkv + D; a.v = qkv + 2 * D; a.o = ctx;
     a.ldq = a.ldk = a.ldv = 3 * D; a.ldo = D;
     a.Tq = T; a.Tk = T; a.q_clip_rows = Ta; a.k_clip_rows = Ta; a.clips = B; a.heads = H; a.head_dim = dh;
     if (rel_tab != nullptr) {
-      SVT_TRY(wavlm_gate(x_rows, M, H, Lw.gate_w2, Lw.gate_b2, Lw.gate_const, tb.gate, s));
+      if (x_stats != nullptr)  // x_rows are un-normalised (LayerNorm fold): normalise inside the gate
+        SVT_TRY(wavlm_gate_ln(x_rows, x_stats, M, H, Lw.gate_w2g, Lw.gate_cg, Lw.gate_dg, Lw.gate_const, eps, tb.gate, s));
+      else
+        SVT_TRY(wavlm_gate(x_rows, M, H, Lw.gate_w2, Lw.gate_b2, Lw.gate_const, tb.gate, s));
       a.rel_tab = rel_tab; a.rel_tab_stride = rel_tab_stride(T); a.gate = tb.gate;
     }
     return attention_bf16(a, s);
@@ -527,8 +554,7 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
   if (want_stats) SVT_CUDA(cudaMemsetAsync(stats_out, 0, 2 * sizeof(double) * (stats_stride > 0 ? B : 1), s));
   const float* final_x = nullptr;
 
-  if (c.stable_layer_norm && get_option_ln_fold() != 0 && c.num_layers > 0 && transformer_rowstats_bytes(e, M) > 0 &&
-      c.rel_pos_buckets == 0) {  // (WavLM's gate needs the normalised rows themselves)
+  if (c.stable_layer_norm && get_option_ln_fold() != 0 && c.num_layers > 0 && transformer_rowstats_bytes(e, M) > 0) {
     // pre-LN layers (HF:612-655) with both per-layer LayerNorms folded around the GEMMs: the GEMM that writes the
     // residual stream also writes its bf16 copy and per-row (sum, sum of squares); the GEMM that reads LN(h) runs on
     // the un-normalised copy with gamma folded into W and finishes the normalisation in its epilogue.
@@ -538,7 +564,7 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
     for (int l = 0; l < c.num_layers; ++l) {
       const svt_encoder::Layer& Lw = e->layers[l];
       SVT_TRY(linear(hb, M, Lw.qkv_ln, nullptr, nullptr, qkv, kActNone, s, nullptr, st, eps));
-      SVT_TRY(attend(Lw, hb));
+      SVT_TRY(attend(Lw, hb, st));
       SVT_TRY(linear(ctx, M, Lw.out, h, h, hb, kActNone, s, st_mid));
       SVT_TRY(linear(hb, M, Lw.ff1_ln, nullptr, nullptr, mid, kActGelu, s, nullptr, st_mid, eps));
       SVT_TRY(linear(mid, M, Lw.ff2, h, h, hb, kActNone, s, st));

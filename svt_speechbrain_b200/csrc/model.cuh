@@ -119,6 +119,9 @@ struct svt_encoder {
     float* gate_w2 = nullptr;
     float* gate_b2 = nullptr;
     float* gate_const = nullptr;
+    float* gate_w2g = nullptr;  // with ln1 folded in: [H][2][64], [H][2], [H][2]
+    float* gate_cg = nullptr;
+    float* gate_dg = nullptr;
   };
   std::vector<float> rel_embed;                 // WavLM: layers.0.attention.rel_attn_embed.weight [buckets][H] (host)
   mutable std::map<int, float*> rel_tabs;       // T -> device table [H][2T - 1] of the Toeplitz position bias (pool-owned)

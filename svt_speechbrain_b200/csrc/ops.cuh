@@ -55,6 +55,10 @@ int layer_norm(const LayerNormArgs& a, cudaStream_t stream);
 // bf16, w2 [2][64] / b2 [2] = gru_rel_pos_linear with its 2 x 4 output groups summed (the sums commute with the Linear)
 int wavlm_gate(const __nv_bfloat16* x, int rows, int heads, const float* w2, const float* b2, const float* head_const,
                float* gate, cudaStream_t stream);
+// the same gate from UN-normalised rows + their folded-LayerNorm statistics (w2g = w2 o gamma per head [heads][2][64], cg its
+// row sums [heads][2], dg = w2 . beta + b2 [heads][2])
+int wavlm_gate_ln(const __nv_bfloat16* x, const float* stats, int rows, int heads, const float* w2g, const float* cg,
+                  const float* dg, const float* head_const, float eps, float* gate, cudaStream_t stream);
 // bucket of a relative position (key - query) as WavLMAttention._relative_positions_bucket computes it in fp32 (host)
 int wavlm_relative_bucket(int relative_position, int num_buckets, int max_distance);
 int row_stats_cast(const float* x, int rows, int D, __nv_bfloat16* y, float* stats, cudaStream_t stream);

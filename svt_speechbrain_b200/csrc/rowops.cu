@@ -507,6 +507,53 @@ __global__ void __launch_bounds__(256) wavlm_gate_kernel(const __nv_bfloat16* __
   }
 }
 
+// WavLM gate with the layer's first LayerNorm folded in (option "ln_fold"): x holds the UN-normalised bf16 rows, stats
+// their [rows][D / 128][2] partial (sum, sum of squares); w2g = w2 o gamma per head [heads][2][64], cg = its row sums
+// [heads][2], dg = w2 . beta + b2 [heads][2]:  w2 . LN(x)_head + b2 = rstd * (w2g . x_head - mean * cg) + dg
+__global__ void __launch_bounds__(256) wavlm_gate_ln_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ stats,
+                                                            int rows, int heads, const float* __restrict__ w2g,
+                                                            const float* __restrict__ cg, const float* __restrict__ dg,
+                                                            const float* __restrict__ head_const, float eps,
+                                                            float* __restrict__ gate) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int D = heads * 64, slots = D / 128;
+  float sum = 0.f, sumsq = 0.f;  // fixed order over the slots, as the GEMM epilogue does
+  for (int j = 0; j < slots; ++j) {
+    const float2 st = *reinterpret_cast<const float2*>(stats + 2 * (static_cast<size_t>(row) * slots + j));
+    sum += st.x; sumsq += st.y;
+  }
+  const float mean = sum / D;
+  const float rstd = rsqrtf(fmaxf(sumsq / D - mean * mean, 0.f) + eps);
+  for (int base = 0; base < D; base += 1024) {
+    const int c0 = base + lane * 32;
+    float a = 0.f, b = 0.f;
+    const int h = c0 >> 6;
+    if (c0 < D) {
+      const __nv_bfloat16* xr = x + static_cast<size_t>(row) * D + c0;
+      const float* wa = w2g + static_cast<size_t>(h) * 128 + (lane & 1) * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 v = ld_bf16x4(xr + i);
+        const float4 pa = __ldg(reinterpret_cast<const float4*>(wa + i));
+        const float4 pb = __ldg(reinterpret_cast<const float4*>(wa + 64 + i));
+        a += v.x * pa.x + v.y * pa.y + v.z * pa.z + v.w * pa.w;
+        b += v.x * pb.x + v.y * pb.y + v.z * pb.z + v.w * pb.w;
+      }
+    }
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    b += __shfl_xor_sync(0xffffffffu, b, 1);
+    if (c0 < D && (lane & 1) == 0) {
+      const float za = rstd * (a - mean * cg[2 * h]) + dg[2 * h];
+      const float zb = rstd * (b - mean * cg[2 * h + 1]) + dg[2 * h + 1];
+      const float ga = 1.f / (1.f + __expf(-za));
+      const float gb = 1.f / (1.f + __expf(-zb));
+      gate[static_cast<size_t>(row) * heads + h] = ga * (gb * head_const[h] - 1.f) + 2.f;
+    }
+  }
+}
+
 template <typename F>
 int dispatch_nv(int D, F&& f) {
   switch (D / 128) {
@@ -540,6 +587,15 @@ int wavlm_gate(const __nv_bfloat16* x, int rows, int heads, const float* w2, con
                float* gate, cudaStream_t stream) {
   if (rows <= 0) return kOk;
   wavlm_gate_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(x, rows, heads, w2, b2, head_const, gate);
+  SVT_POST_LAUNCH();
+  return kOk;
+}
+
+int wavlm_gate_ln(const __nv_bfloat16* x, const float* stats, int rows, int heads, const float* w2g, const float* cg,
+                  const float* dg, const float* head_const, float eps, float* gate, cudaStream_t stream) {
+  if (rows <= 0) return kOk;
+  if (heads % 2 != 0) return fail(kInvalidArgument, "wavlm_gate_ln: the statistics slots need heads * 64 % 128 == 0");
+  wavlm_gate_ln_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(x, stats, rows, heads, w2g, cg, dg, head_const, eps, gate);
   SVT_POST_LAUNCH();
   return kOk;
 }

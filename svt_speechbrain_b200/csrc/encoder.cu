@@ -376,7 +376,7 @@ int svt::encoder_finalize(svt_encoder* e) {
     }
     e->layers.push_back(L);
   }
-  e->rel_tabs.clear();  // device tables belonged to the pool released above
+  e->drop_rel_tabs();  // built from the previous weights
   e->rel_embed.clear();
   if (c.rel_pos_buckets > 0) {
     const RawTensor* emb;
@@ -529,8 +529,12 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
         for (int hh = 0; hh < H; ++hh)
           tab[static_cast<size_t>(hh) * stride + d + T - 1] = e->rel_embed[static_cast<size_t>(bucket) * H + hh];
       }
+      if (e->rel_tabs.size() >= svt_encoder::kMaxRelTabs) {  // many distinct clip lengths: start the cache over
+        SVT_CUDA(cudaStreamSynchronize(s));
+        e->drop_rel_tabs();
+      }
       float* dev = nullptr;
-      SVT_TRY(const_cast<svt_encoder*>(e)->pool.alloc_t<float>(tab.size(), &dev));
+      SVT_CUDA(cudaMalloc(&dev, sizeof(float) * tab.size()));
       SVT_CUDA(cudaMemcpyAsync(dev, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, s));
       SVT_CUDA(cudaStreamSynchronize(s));  // `tab` is pageable host memory going out of scope
       it = e->rel_tabs.emplace(T, dev).first;

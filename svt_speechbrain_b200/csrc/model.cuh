@@ -86,6 +86,11 @@ struct svt_encoder {
   ~svt_encoder() {
     if (head_w != nullptr) cudaFree(head_w);
     if (head_b != nullptr) cudaFree(head_b);
+    drop_rel_tabs();
+  }
+  void drop_rel_tabs() const {
+    for (auto& kv : rel_tabs) cudaFree(kv.second);
+    rel_tabs.clear();
   }
   svt_encoder_config cfg{};
   svt::WeightRegistry reg;
@@ -124,7 +129,9 @@ struct svt_encoder {
     float* gate_dg = nullptr;
   };
   std::vector<float> rel_embed;                 // WavLM: layers.0.attention.rel_attn_embed.weight [buckets][H] (host)
-  mutable std::map<int, float*> rel_tabs;       // T -> device table [H][2T - 1] of the Toeplitz position bias (pool-owned)
+  mutable std::map<int, float*> rel_tabs;       // T -> device table [H][stride] of the Toeplitz position bias (own cudaMalloc,
+                                                // at most kMaxRelTabs clip lengths cached)
+  static constexpr size_t kMaxRelTabs = 32;
   std::vector<Layer> layers;
   float* head_w = nullptr;  // [n_out, D] fp32
   float* head_b = nullptr;

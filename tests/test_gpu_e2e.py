@@ -409,3 +409,21 @@ def test_wavlm_position_bias_in_both_attention_kernels():
     finally:
         lib().svt_set_option(b"attention_impl", 0)
     assert float((outs[1] - outs[2]).abs().max()) < 5e-2
+
+
+def test_wavlm_bias_table_cache_is_bounded():
+    """The per-clip-length position-bias tables are cached (at most 32 lengths): 40 different lengths force a reset of
+    the cache, after which an earlier length gives bit-identical logits again."""
+    from oracle import wav2vec2_oracle as wo
+    import svt_speechbrain_b200 as svt
+
+    cfg = wo.W2V2Config.wavlm_base()
+    lobe, lin, sd, head = _build(cfg)
+    tr = svt.AMTTranscriber(lobe, lin)
+    g = torch.Generator().manual_seed(2)
+    first = torch.randn(1, 4000, generator=g).cuda()
+    ref = tr.logits(first).clone()
+    for i in range(40):
+        out = tr.logits(torch.randn(1, 4000 + 320 * (i + 1), generator=g).cuda())
+        assert torch.isfinite(out).all()
+    assert torch.equal(tr.logits(first), ref)

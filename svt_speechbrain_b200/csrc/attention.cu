@@ -249,11 +249,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
 template <int DH>
 int launch_attention(const AttentionArgs& a, cudaStream_t stream) {
   const int smem = (kBQ + 4 * kBK) * DH * 2;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SVT_CUDA(cudaFuncSetAttribute(attention_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_seen{0};
+  if (first_use_on_device(attr_seen)) SVT_CUDA(cudaFuncSetAttribute(attention_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid(ceil_div(a.Tq, kBQ), a.heads, a.clips);
   attention_kernel<DH><<<grid, kAttnThreads, smem, stream>>>(a.q, a.k, a.v, a.o, a.ldq, a.ldk, a.ldv, a.ldo, a.Tq, a.Tk,
                                                              a.q_clip_rows, a.k_clip_rows, a.rel_tab, a.gate, a.heads, a.rel_tab_stride);

@@ -508,11 +508,8 @@ int attention_bf16_tc(const AttentionArgs& a, cudaStream_t stream) {
     SVT_TRY(encode_bf16_map(&tmK, a.k, 3, dims, strk, box));
     SVT_TRY(encode_bf16_map(&tmV, a.v, 3, dims, strv, box));
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    SVT_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_seen{0};
+  if (first_use_on_device(attr_seen)) SVT_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc));
   const int n_qpairs = ceil_div(a.Tq, 2 * kTileQ);
   const int n_items = n_qpairs * a.heads * a.clips;
   const int grid = n_items < num_sms() ? n_items : num_sms();

@@ -1,5 +1,6 @@
 // Shared helpers for the sm_100a kernels: error plumbing, PTX wrappers (mbarrier, TMA, tcgen05).
 #pragma once
+#include <atomic>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -51,6 +52,14 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 void note_kernel_launch();
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+// true the first time it is called with `seen` on the current device: per-kernel function attributes (dynamic shared
+// memory size) are per device, and one process may drive several GPUs (one handle per GPU)
+inline bool first_use_on_device(std::atomic<unsigned long long>& seen) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  const unsigned long long bit = 1ull << (dev & 63);
+  return (seen.fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+}
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------

@@ -362,11 +362,8 @@ int launch(const GemmArgs& g, const KParams& kp, cudaStream_t stream) {
   const uint64_t ws[1] = {static_cast<uint64_t>(g.w_cols)};
   const uint32_t wb[2] = {BK, BN};
   SVT_TRY(encode_bf16_map(&tmB, g.w, 2, wd, ws, wb));
-  static bool attr_set = false;
-  if (!attr_set) {
-    SVT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_seen{0};
+  if (first_use_on_device(attr_seen)) SVT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
   const int tiles = kp.m_tiles * kp.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, kp);

@@ -259,11 +259,8 @@ int gemm_bf16_tc_pair(const GemmArgs& g, cudaStream_t stream) {
   const uint64_t ws[1] = {static_cast<uint64_t>(g.w_cols)};
   const uint32_t wb[2] = {BK, BN2 / 2};
   SVT_TRY(encode_bf16_map(&tmB, g.w, 2, wd, ws, wb));
-  static bool attr_set = false;
-  if (!attr_set) {
-    SVT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_seen{0};
+  if (first_use_on_device(attr_seen)) SVT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
   const int m_pairs = ceil_div(g.M, 2 * BM);
   const int n_tiles = g.N / BN2;
   const int tiles = m_pairs * n_tiles;

@@ -689,11 +689,8 @@ int head_forward(const HeadArgs& a, cudaStream_t stream) {
     size_t smem = (a.w != nullptr) ? sizeof(float) * a.n_out * a.D : 0;
     int w_in_smem = 1;
     if (smem > 160 * 1024) { smem = 0; w_in_smem = 0; }
-    static bool attr_set = false;
-    if (!attr_set) {
-      SVT_CUDA(cudaFuncSetAttribute(head_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_seen{0};
+    if (first_use_on_device(attr_seen)) SVT_CUDA(cudaFuncSetAttribute(head_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     int grid = ceil_div(a.clips * a.T, 8 * head_rows(NV));
     if (grid > num_sms()) grid = num_sms();
     head_kernel<NV><<<grid, 256, smem, stream>>>(a.x, a.clips, a.clip_rows, a.T, a.stats, a.eps, a.w, a.b, a.n_out,

@@ -159,3 +159,39 @@ def test_eval_transform_matches_reference_compose():
         assert np.abs(got[0, 0].cpu().numpy() - x).max() < 1e-6
     with pytest.raises(RuntimeError):
         vt.eval_transform(torch.zeros(2, 96, 96, dtype=torch.uint8))
+
+
+def test_stage_c_from_cached_features(tmp_path):
+    """feature_cache.transcribe_from_cache: cached per-song audio / video features -> utterance slicing of the reference
+    recipe -> FusionRCA + head (batched) -> one decode == the same utterances pushed one by one (train_rca_av.py:28-51)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    import svt_speechbrain_b200 as svt
+    from oracle import make_golden as mg
+    from oracle import wav2vec2_oracle as wo
+    from svt_speechbrain_b200 import feature_cache as fc
+
+    fus = svt.FusionRCA()
+    full = dict(fus.state_dict())
+    full.update(mg.random_fusion_weights(1024, 3072, seed=3))
+    fus.load_state_dict(full, strict=True)
+    fus = fus.cuda()
+    lin = svt.Linear(n_neurons=20, input_size=1024)
+    lin.load_state_dict(wo.random_head(1024, 20, seed=0))
+    lin = lin.cuda()
+    g = torch.Generator().manual_seed(4)
+    audio = torch.randn(611, 1024, generator=g)    # 12.3 s of 49.8 fps features -> utterances of 249 / 249 / 113 frames
+    video = torch.randn(600, 1024, generator=g)    # shorter than the audio: the last utterance is zero-padded
+    pa = fc.save_song_features(audio, fc.audio_feats_path(str(tmp_path / "s")))
+    pv = fc.save_song_features(video, fc.video_feats_path(str(tmp_path / "s")))
+    dec = svt.AMTTranscriber.__new__(svt.AMTTranscriber)
+    dec.hp = svt.AMTHparams()
+    notes = fc.transcribe_from_cache(fus, lin, dec, pa, pv, utter_num=3)
+    pieces = []
+    for u in (1, 2, 3):
+        a, v = fc.load_av_utterance(pa, pv, u, 3)
+        assert a.shape == v.shape
+        pieces.append(lin(fus(a[None].cuda(), v[None].cuda()))[0])
+    want = dec.decode(torch.cat(pieces))
+    assert sum(p.shape[0] for p in pieces) == 611
+    assert notes.shape == want.shape and np.allclose(notes, want)

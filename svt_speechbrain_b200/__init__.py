@@ -9,7 +9,8 @@ Reference-shaped modules (same names, constructor kwargs, forward signatures and
 All arithmetic runs in the C-ABI library libsvt_b200.so (include/svt_b200.h); there is no CPU fallback.
 """
 from ._lib import LIB_PATH, SvtError, lib  # noqa: F401
-from .amt import AMTHparams, AMTTranscriber, AVTranscriber, split_song, split_song_overlapped, stitch_plan  # noqa: F401
+from .amt import (AMTHparams, AMTTranscriber, AVTranscriber, decode_logits, frame_info, split_song,  # noqa: F401
+                  split_song_overlapped, stitch_plan)
 from .fairseq_interface import FairseqAVHubertPretrain  # noqa: F401
 from .fusion import FusionRCA  # noqa: F401
 from .huggingface_interface import HuggingFaceWav2Vec2  # noqa: F401

@@ -47,6 +47,30 @@ def split_song(n_samples: int, hp: AMTHparams, dur: Optional[float] = None) -> L
     return out
 
 
+def frame_info(logits: torch.Tensor, hp: "AMTHparams"):
+    """(n_frames, 20) CUDA logits -> host arrays (p_on f32, p_off f32, octave i32, pitch_class i32)
+    (train_audio_ssl.py:93-100).  argmax runs on the device (first max wins); the two sigmoids are taken on the HOST
+    with torch so the probabilities are bit-identical to the CPU reference that frame2note's `==` / `>=` tests see."""
+    lg = logits.reshape(-1, logits.shape[-1]).contiguous()
+    n = lg.shape[0]
+    octv = torch.empty(n, dtype=torch.int32, device=lg.device)
+    pc = torch.empty(n, dtype=torch.int32, device=lg.device)
+    with torch.cuda.device(lg.device):
+        check(lib().svt_frame_postproc(ptr(lg), n, lg.shape[1], 2, hp.pitch_octave_num + 1,
+                                       2 + hp.pitch_octave_num + 1, hp.pitch_class_num + 1, ptr(octv), ptr(pc),
+                                       current_stream_ptr()))
+    on_off = lg[:, :2].cpu()
+    p = torch.sigmoid(on_off)
+    return p[:, 0].contiguous().numpy(), p[:, 1].contiguous().numpy(), octv.cpu().numpy(), pc.cpu().numpy()
+
+
+def decode_logits(logits: torch.Tensor, hp: "AMTHparams") -> np.ndarray:
+    """(n_frames, 20) logits of ONE song (utterances already concatenated in order) -> (n_notes, 3) float64
+    [onset s, offset s, MIDI pitch] (frame2note, utils.py:82-149)."""
+    p_on, p_off, octv, pc = frame_info(logits, hp)
+    return decode_arrays(p_on, p_off, octv, pc, hp.onset_threshold, hp.offset_threshold, 1.0 / hp.frame_rate)
+
+
 FRAME_HOP = 320      # samples between output frames of the conv stack (product of the strides 5 * 2^6)
 FRAME_FIELD = 400    # receptive field of one output frame
 
@@ -139,27 +163,11 @@ class AMTTranscriber:
         return out
 
     def frame_info(self, logits: torch.Tensor):
-        """(n_frames, 20) CUDA logits -> host arrays (p_on f32, p_off f32, octave i32, pitch_class i32).
-        argmax runs on the device (first max wins); the two sigmoids are taken on the HOST with torch so the
-        probabilities are bit-identical to the CPU reference that frame2note's `==` / `>=` tests see."""
-        lg = logits.reshape(-1, logits.shape[-1]).contiguous()
-        n = lg.shape[0]
-        octv = torch.empty(n, dtype=torch.int32, device=lg.device)
-        pc = torch.empty(n, dtype=torch.int32, device=lg.device)
-        hp = self.hp
-        with torch.cuda.device(lg.device):
-            check(lib().svt_frame_postproc(ptr(lg), n, lg.shape[1], 2, hp.pitch_octave_num + 1,
-                                           2 + hp.pitch_octave_num + 1, hp.pitch_class_num + 1, ptr(octv), ptr(pc),
-                                           current_stream_ptr()))
-        on_off = lg[:, :2].cpu()
-        p = torch.sigmoid(on_off)
-        return p[:, 0].contiguous().numpy(), p[:, 1].contiguous().numpy(), octv.cpu().numpy(), pc.cpu().numpy()
+        return frame_info(logits, self.hp)
 
     def decode(self, logits: torch.Tensor) -> np.ndarray:
         """(n_frames, 20) logits of ONE song (utterances already concatenated in order) -> (n_notes, 3) float64."""
-        p_on, p_off, octv, pc = self.frame_info(logits)
-        return decode_arrays(p_on, p_off, octv, pc, self.hp.onset_threshold, self.hp.offset_threshold,
-                             1.0 / self.hp.frame_rate)
+        return decode_logits(logits, self.hp)
 
     @torch.no_grad()
     def transcribe_song(self, wav: torch.Tensor, dur: Optional[float] = None, batch_clips: int = 64,
@@ -233,8 +241,6 @@ class AVTranscriber:
         self.audio_lobe, self.video_lobe, self.fusion, self.head = audio_lobe, video_lobe, fusion, head
         self.hp = hparams or AMTHparams()
         self.device = torch.device(device)
-        self._decoder = AMTTranscriber.__new__(AMTTranscriber)
-        self._decoder.hp = self.hp
         self.concurrent_streams = True  # run the two encoders on two CUDA streams (their small-batch grids leave SMs idle)
         self._side_stream = None
 
@@ -260,4 +266,4 @@ class AVTranscriber:
         return self.head(self.fusion(a, v))
 
     def decode(self, logits: torch.Tensor) -> np.ndarray:
-        return self._decoder.decode(logits)
+        return decode_logits(logits, self.hp)

@@ -132,12 +132,13 @@ def slice_av_utterance(sig1: torch.Tensor, sig2: torch.Tensor, utter_id: int, ut
 
 
 @torch.no_grad()
-def transcribe_from_cache(fusion, head, decoder, audio_path: str, video_path: str, utter_num: int,
+def transcribe_from_cache(fusion, head, hparams: Optional[AMTHparams], audio_path: str, video_path: str, utter_num: int,
                           dur_threshold: float = 5, device="cuda", batch_utterances: int = 32) -> np.ndarray:
     """Stage C evaluation for one song from the cached features: every utterance through FusionRCA + head (the
     reference does it one utterance per step, train_rca_av.py:28-51,84-112), frames concatenated in utterance order,
-    one decode.  Utterances of equal frame counts are batched (FusionRCA has no cross-clip coupling).
-    decoder: an AMTTranscriber / AVTranscriber (only .decode is used)."""
+    one decode.  Utterances of equal frame counts are batched (FusionRCA has no cross-clip coupling)."""
+    from .amt import decode_logits
+
     dev = torch.device(device)
     sig1 = torch.load(audio_path)
     sig2 = torch.load(video_path)
@@ -156,7 +157,7 @@ def transcribe_from_cache(fusion, head, decoder, audio_path: str, video_path: st
         for k, u in enumerate(order[i:j]):
             out[u] = lg[k]
         i = j
-    return decoder.decode(torch.cat(out, dim=0))
+    return decode_logits(torch.cat(out, dim=0), hparams or AMTHparams())
 
 
 def iter_song_utterances(n_samples: int, hparams: Optional[AMTHparams] = None,

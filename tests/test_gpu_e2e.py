@@ -152,11 +152,7 @@ def test_notes_bit_exact_from_identical_logits():
     fi = [(p_on[i], p_off[i], int(octv[i]), int(pc[i])) for i in range(n)]
     want = np.array(f2n_oracle(fi, 0.4, 0.5, 1 / 49.8), dtype=np.float64).reshape(-1, 3)
 
-    class _Head:  # minimal stand-in: decode() only needs hparams
-        pass
-    tr = svt.AMTTranscriber.__new__(svt.AMTTranscriber)
-    tr.hp = svt.AMTHparams()
-    got = tr.decode(logits.cuda())
+    got = svt.decode_logits(logits.cuda(), svt.AMTHparams())
     assert got.shape == want.shape and np.array_equal(got, want)
     assert len(want) > 50
 

@@ -184,14 +184,13 @@ def test_stage_c_from_cached_features(tmp_path):
     video = torch.randn(600, 1024, generator=g)    # shorter than the audio: the last utterance is zero-padded
     pa = fc.save_song_features(audio, fc.audio_feats_path(str(tmp_path / "s")))
     pv = fc.save_song_features(video, fc.video_feats_path(str(tmp_path / "s")))
-    dec = svt.AMTTranscriber.__new__(svt.AMTTranscriber)
-    dec.hp = svt.AMTHparams()
-    notes = fc.transcribe_from_cache(fus, lin, dec, pa, pv, utter_num=3)
+    from svt_speechbrain_b200.amt import decode_logits
+    notes = fc.transcribe_from_cache(fus, lin, svt.AMTHparams(), pa, pv, utter_num=3)
     pieces = []
     for u in (1, 2, 3):
         a, v = fc.load_av_utterance(pa, pv, u, 3)
         assert a.shape == v.shape
         pieces.append(lin(fus(a[None].cuda(), v[None].cuda()))[0])
-    want = dec.decode(torch.cat(pieces))
+    want = decode_logits(torch.cat(pieces), svt.AMTHparams())
     assert sum(p.shape[0] for p in pieces) == 611
     assert notes.shape == want.shape and np.allclose(notes, want)

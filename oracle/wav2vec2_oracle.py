@@ -17,8 +17,9 @@ The functions take a plain dict of fp32 tensors keyed by the reference's state_d
 names (prefix "model." as saved by the lobe) so the same weights feed the oracle,
 the reference (when importable) and the CUDA path.
 
-Pinned against the imported reference by tests/test_oracle_vs_reference.py (runs only
-where /root/reference exists) and by the committed fixtures in tests/golden/.
+Pinned against outputs of the imported reference: oracle/make_golden.py (run in the authoring container,
+where /root/reference exists) wrote the fixtures under tests/golden/, and tests/test_oracle_golden.py checks
+this module against them on the CPU.
 """
 from __future__ import annotations
 

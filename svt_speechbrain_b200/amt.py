@@ -86,6 +86,9 @@ def split_song_overlapped(n_samples: int, sample_rate: int, dur: float, overlap:
     out, a = [], 0
     while True:
         b = min(a + win, n_samples)
+        if out and b - a < FRAME_FIELD:  # a tail too short for one frame: the previous window takes it (as the reference's
+            out[-1] = (out[-1][0], n_samples)  # last utterance takes the remainder, prepare_benchmarks.py:124-127)
+            return out
         out.append((a, b))
         if b >= n_samples:
             return out
@@ -145,7 +148,8 @@ class AMTTranscriber:
     def _clip_logits(self, clips: Sequence[torch.Tensor], batch_clips: int, per_clip_norm: bool) -> List[torch.Tensor]:
         """Frame logits (T_i, 20) of 1-D clips, in order.  Runs of consecutive equal-length clips go through the encoder
         as one batch of at most `batch_clips`; with per_clip_norm every clip is normalised on its own (the reference's
-        batch-size-1 evaluation), which needs 16-byte aligned clips inside a batch -- otherwise one call per clip."""
+        batch-size-1 evaluation).  Clips shorter than the conv stack's receptive field have no frame: they yield an empty
+        (0, n_out) tensor instead of reaching the encoder (so a ragged tail never raises on one rank only)."""
         out: List[torch.Tensor] = []
         i = 0
         while i < len(clips):
@@ -153,11 +157,13 @@ class AMTTranscriber:
             L = clips[i].numel()
             while j < len(clips) and j - i < batch_clips and clips[j].numel() == L:
                 j += 1
+            if L < FRAME_FIELD:
+                out.extend(torch.empty(0, self.hp.n_out, dtype=torch.float32, device=self.device) for _ in range(j - i))
+                i = j
+                continue
             batch = torch.stack(list(clips[i:j]))
-            if per_clip_norm and j - i > 1 and L % 4 != 0:
-                lg = torch.cat([self.logits(c.unsqueeze(0)) for c in batch], dim=0)
-            else:  # a single clip is its own normalisation scope either way
-                lg = self.logits(batch, per_clip_norm=per_clip_norm and j - i > 1)
+            # a single clip is its own normalisation scope either way
+            lg = self.logits(batch, per_clip_norm=per_clip_norm and j - i > 1)
             out.extend(lg[k] for k in range(lg.shape[0]))
             i = j
         return out

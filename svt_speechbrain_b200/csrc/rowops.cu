@@ -97,22 +97,33 @@ layer_norm_kernel(const float* __restrict__ xf, const __nv_bfloat16* __restrict_
 }
 
 // ------------------------------------------------------------------------------------ tensor stats
-// blockIdx.y = segment (clip): x + y * seg_stride, stats + y * stats_stride (both 0 for the whole-tensor form)
+// blockIdx.y = segment (clip): x + y * seg_stride, stats + y * stats_stride (both 0 for the whole-tensor form).
+// A segment may start at any 4-byte address (a row of a batch whose length is not a multiple of 4, a sliced view of a
+// song): up to 3 leading scalars bring the body to a 16-byte boundary, the remainder is a scalar tail.
 __global__ void __launch_bounds__(256) tensor_stats_kernel(const float* __restrict__ x, size_t n, double* stats,
                                                            size_t seg_stride, int stats_stride) {
   x += static_cast<size_t>(blockIdx.y) * seg_stride;
   stats += static_cast<size_t>(blockIdx.y) * stats_stride;
+  size_t head = ((16 - (reinterpret_cast<uintptr_t>(x) & 15)) & 15) >> 2;
+  if (head > n) head = n;
+  const float* xa = x + head;
+  const size_t nb = n - head;
   float s = 0.f, ss = 0.f;
-  const size_t n4 = n / 4;
+  const size_t n4 = nb / 4;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xa) + i);
     s += (v.x + v.y) + (v.z + v.w);
     ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
   }
-  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
-    const float v = x[n4 * 4 + threadIdx.x];
-    s += v; ss += v * v;
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < head) {
+      const float v = x[threadIdx.x];
+      s += v; ss += v * v;
+    } else if (threadIdx.x >= 4 && threadIdx.x - 4 < (nb & 3)) {
+      const float v = xa[n4 * 4 + threadIdx.x - 4];
+      s += v; ss += v * v;
+    }
   }
   __shared__ double sh[8];
   const double a = block_sum_double(static_cast<double>(s), sh);
@@ -632,7 +643,7 @@ int ln_fold_vectors(const float* w_f32, const __nv_bfloat16* w_packed, const flo
 
 int tensor_stats(const float* x, size_t n, double* stats, cudaStream_t stream) {
   SVT_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(double), stream));
-  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return fail(kInvalidArgument, "tensor_stats: input must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(x) & 3) != 0) return fail(kInvalidArgument, "tensor_stats: input must be 4-byte aligned");
   const int grid = num_sms() * 4;
   tensor_stats_kernel<<<grid, 256, 0, stream>>>(x, n, stats, 0, 0);
   SVT_POST_LAUNCH();
@@ -641,8 +652,7 @@ int tensor_stats(const float* x, size_t n, double* stats, cudaStream_t stream) {
 
 int tensor_stats_per_clip(const float* x, int clips, size_t n_per_clip, double* stats, cudaStream_t stream) {
   SVT_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(double) * clips, stream));
-  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (clips > 1 && n_per_clip % 4 != 0))
-    return fail(kInvalidArgument, "per-clip statistics need 16-byte aligned clips (n_samples % 4 == 0)");
+  if ((reinterpret_cast<uintptr_t>(x) & 3) != 0) return fail(kInvalidArgument, "tensor_stats: input must be 4-byte aligned");
   // CTAs per clip depend on the clip length only, never on the batch: a clip's partial sums (and so its statistics and
   // everything downstream) are the same whichever batch or rank it is processed in
   int gx = static_cast<int>(std::min<size_t>((n_per_clip / 4 + 4095) / 4096, 1024));

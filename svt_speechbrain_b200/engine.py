@@ -28,10 +28,14 @@ def encoder_config_from_hf(cfg, normalize_wav: bool, output_norm: bool) -> Encod
         c.conv_kernel[i] = k
         c.conv_stride[i] = s
     c.conv_bias = int(bool(cfg.conv_bias))
-    if cfg.feat_extract_norm not in ("layer", "group"):
-        raise ValueError(f"feat_extract_norm={cfg.feat_extract_norm!r}")
-    c.feat_norm_layer = int(cfg.feat_extract_norm == "layer")
-    c.stable_layer_norm = int(bool(cfg.do_stable_layer_norm))
+    # Data2VecAudioConfig defines neither field: its feature extractor is always the layer-norm variant and its encoder
+    # post-LN (HF modeling_data2vec_audio.py: Data2VecAudioConvLayer, Data2VecAudioEncoder)
+    data2vec = type(cfg).__name__.startswith("Data2Vec")
+    feat_norm = getattr(cfg, "feat_extract_norm", "layer" if data2vec else "group")
+    if feat_norm not in ("layer", "group"):
+        raise ValueError(f"feat_extract_norm={feat_norm!r}")
+    c.feat_norm_layer = int(feat_norm == "layer")
+    c.stable_layer_norm = int(bool(getattr(cfg, "do_stable_layer_norm", False)))
     if type(cfg).__name__.startswith("Data2Vec"):  # stack of num_conv_pos_embeddings convs of conv_pos_kernel_size taps
         c.pos_conv_kernel = cfg.conv_pos_kernel_size
         c.pos_conv_layers = cfg.num_conv_pos_embeddings

@@ -124,17 +124,29 @@ class FairseqAVHubertPretrain(nn.Module):
         super().__init__()
         cfg = dict(_LARGE)
         state = None
-        if pretrained_path is not None and os.path.exists(str(pretrained_path)):
+        # the reference first brings the checkpoint to `save_path` (speechbrain download_file: an existing destination is
+        # kept, a local source is copied, a URL is fetched -- :399) and then loads `save_path` (:414-420)
+        ckpt_path = None
+        if save_path is not None and os.path.isfile(str(save_path)):
+            ckpt_path = str(save_path)
+        elif pretrained_path is not None and os.path.isfile(str(pretrained_path)):
+            ckpt_path = str(pretrained_path)
+            if save_path is not None:
+                import shutil
+                os.makedirs(os.path.dirname(os.path.abspath(str(save_path))), exist_ok=True)
+                shutil.copyfile(ckpt_path, str(save_path))
+                ckpt_path = str(save_path)
+        if ckpt_path is not None:
             try:
-                ckpt = torch.load(pretrained_path, map_location="cpu", weights_only=False)
+                ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
             except ModuleNotFoundError as e:  # fairseq checkpoints pickle an omegaconf config
-                raise ImportError(f"reading {pretrained_path} needs the package its config was pickled with ({e.name}); "
+                raise ImportError(f"reading {ckpt_path} needs the package its config was pickled with ({e.name}); "
                                   "re-save the checkpoint as {'model': state_dict} to load it without fairseq") from e
             cfg = _cfg_from_checkpoint(ckpt)
             state = ckpt["model"] if isinstance(ckpt, dict) and "model" in ckpt else ckpt
         elif pretrain:
-            raise FileNotFoundError(f"{pretrained_path} does not exist (remote fetching is not built; download the AV-HuBERT "
-                                    "checkpoint first)")
+            raise FileNotFoundError(f"neither save_path={save_path!r} nor pretrained_path={pretrained_path!r} is a local file "
+                                    "(fetching a URL needs network access: download the AV-HuBERT checkpoint first)")
         if model_config:
             cfg.update(model_config)
         self.model = _AVHubert(cfg)
@@ -145,7 +157,7 @@ class FairseqAVHubertPretrain(nn.Module):
             missing = [k for k in own if k not in picked and not k.endswith("num_batches_tracked") and
                        not k.startswith("feature_extractor_audio.") and k != "mask_emb"]
             if missing:
-                raise RuntimeError(f"checkpoint {pretrained_path} lacks {len(missing)} tensors, e.g. {missing[:3]}")
+                raise RuntimeError(f"checkpoint {ckpt_path} lacks {len(missing)} tensors, e.g. {missing[:3]}")
             self.model.load_state_dict(picked, strict=False)
         self.freeze = freeze
         self.normalize = bool(input_norm)  # the reference resolves input_norm=None from the task config (:423-429)

@@ -55,8 +55,7 @@ class HuggingFaceWav2Vec2(nn.Module):
         config = config_cls.from_pretrained(source, cache_dir=save_path)
         config.apply_spec_augment = apply_spec_augment  # inert at eval (HF:1292)
         if pretrain:
-            self._check_model_source(source)
-            self.model = model_cls.from_pretrained(source, config=config, cache_dir=save_path)
+            self._from_pretrained(source, config, model_cls, save_path)
         else:
             self.model = model_cls(config)
         self.normalize_wav = self.feature_extractor.do_normalize
@@ -74,15 +73,48 @@ class HuggingFaceWav2Vec2(nn.Module):
         self._engine = None
         self._engine_key = None
 
+    def _from_pretrained(self, source, config, model_cls, save_path):
+        """Reference :161-179: a SpeechBrain-pretrained checkpoint (`*.ckpt`, written by HuggingFaceWav2Vec2Pretrain) is
+        loaded into a model built from the config; anything else goes through HF `from_pretrained`."""
+        is_sb, ckpt_file = self._check_model_source(source)
+        if is_sb:
+            self.model = model_cls(config)
+            self.model.gradient_checkpointing_disable()
+            self._load_sb_pretrained_w2v2_parameters(ckpt_file)
+        else:
+            self.model = model_cls.from_pretrained(source, config=config, cache_dir=save_path)
+
+    def _load_sb_pretrained_w2v2_parameters(self, path):
+        """Reference :181-217: keys of a SpeechBrain pre-training checkpoint carry one extra level, `model.wav2vec2.<hf name>`;
+        strip it, load non-strictly, warn about what did not transfer."""
+        import logging
+
+        log = logging.getLogger(__name__)
+        orig = torch.load(path, map_location="cpu")
+        modified = {k.replace("model.wav2vec2.", ""): v for k, v in orig.items() if "wav2vec2." in k}
+        incompatible = self.model.load_state_dict(modified, strict=False)
+        for k in incompatible.missing_keys:
+            log.warning(f"During parameter transfer to {type(self.model).__name__} loading from {path}, the transferred "
+                        f"parameters did not have parameters for the key: {k}")
+        for k in incompatible.unexpected_keys:
+            log.warning(f"The param with the key: {k} is discarded as it is useless for wav2vec 2.0 finetuning.")
+
     @staticmethod
     def _check_model_source(path):
-        """Reference :181-261: a local directory must hold a HF (*.bin / *.safetensors) or SB (*.ckpt) checkpoint."""
+        """Reference :219-261 -> (is_sb, checkpoint_filename).  A local directory holding a HF checkpoint (`*.bin`, or the
+        `*.safetensors` newer transformers write) is HF; one holding a `*.ckpt` is SpeechBrain-pretrained; a local directory
+        with neither raises FileNotFoundError.  A path that does not exist locally is a hub id: the reference asks the hub
+        for its file list (`model_info`); there is no network here, so it is handed to HF `from_pretrained` as is."""
         source = pathlib.Path(path)
-        if source.exists():
-            for f in os.listdir(path):
-                if f.endswith((".bin", ".safetensors", ".ckpt")):
-                    return
-            raise FileNotFoundError(f"{path} does not contain a .bin or .ckpt checkpoint !")
+        if not source.exists():
+            return False, ""
+        files = sorted(os.listdir(path))
+        if any(f.endswith((".bin", ".safetensors")) for f in files):
+            return False, ""
+        for f in files:
+            if f.endswith(".ckpt"):
+                return True, os.path.join(path, f)
+        raise FileNotFoundError(f"{path} does not contain a .bin or .ckpt checkpoint !")
 
     # ------------------------------------------------------------------ engine management
     def _weights_key(self):

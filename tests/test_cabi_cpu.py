@@ -121,3 +121,36 @@ def test_wavlm_relative_bucket_matches_torch():
     for d in range(T):
         assert L.svt_wavlm_relative_bucket(d, cfg.num_buckets, cfg.max_bucket_distance) == int(b[0, d])
         assert L.svt_wavlm_relative_bucket(-d, cfg.num_buckets, cfg.max_bucket_distance) == int(b[d, 0])
+
+
+def _header_struct_fields(name):
+    """Field names of `typedef struct <name> { ... }` in include/svt_b200.h, in order (comments stripped)."""
+    hdr = open(os.path.join(ROOT, "include", "svt_b200.h")).read()
+    body = re.search(r"typedef struct " + name + r" \{(.*?)\} " + name + r";", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    return [re.match(r"\s*(?:const\s+)?\w+\s+(\w+)", d).group(1) for d in body.split(";") if d.strip()]
+
+
+def test_ctypes_structs_follow_the_header_field_for_field():
+    for cname, cls in (("svt_encoder_config", _lib.EncoderConfig), ("svt_fusion_config", _lib.FusionConfig),
+                       ("svt_video_config", _lib.VideoConfig)):
+        assert _header_struct_fields(cname) == [f[0] for f in cls._fields_], cname
+
+
+def test_integration_md_ctypes_stub_runs():
+    """INTEGRATION.md's ctypes stub is the reference-side binding a maintainer would add; everything above its
+    'a B200 is needed' marker must execute as written (struct layout, config construction, host-only entry points)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(import ctypes as C, os\n.*?)```", text, re.S).group(1)
+    head, marker, _ = block.partition("# ---- from here on a B200 is needed")
+    assert marker
+    env = {}
+    os.environ["SVT_B200_LIB"] = svt.LIB_PATH
+    try:
+        exec(compile(head, "INTEGRATION.md", "exec"), env)
+    finally:
+        os.environ.pop("SVT_B200_LIB", None)
+    assert env["T"] == 499
+    assert C.sizeof(env["EncoderConfig"]) == C.sizeof(_lib.EncoderConfig)
+    assert [f[0] for f in env["EncoderConfig"]._fields_] == [f[0] for f in _lib.EncoderConfig._fields_]
+    env["L"].svt_encoder_destroy(env["h"])

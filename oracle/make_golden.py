@@ -204,7 +204,7 @@ def gold_frame2note():
     print("frame2note cases", len(cases))
 
 
-def gold_avhubert_resnet(name, B, T, seed=5):
+def gold_avhubert_resnet(name, B, T, seed=5, col_step=1):
     """Reference ResEncoder (N20EMv2/video_only/resnet.py:133-171) on seeded weights (avhubert_oracle.random_weights,
     BN with non-trivial running statistics) and a seeded normalised-video-like input."""
     from .avhubert_oracle import AVHubertConfig, random_weights as av_weights
@@ -222,9 +222,65 @@ def gold_avhubert_resnet(name, B, T, seed=5):
     video = torch.randn(B, 1, T, 88, 88, generator=g)
     with torch.no_grad():
         out = ref(video)  # (B, 512, T)
+    extra = {} if col_step == 1 else {"col_step": col_step, "frame_sum": out.double().sum(1).numpy(),
+                                      "frame_sumsq": (out.double() ** 2).sum(1).numpy()}
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), B=B, T=T, weight_seed=seed, video_seed=seed + 100,
-                        out=out.numpy())
+                        out=out[:, ::col_step].numpy(), **extra)
     print(name, tuple(out.shape), "absmax", float(out.abs().max()))
+
+
+def bench_wav(B, L, seed=1986):
+    """Synthetic clips of different loudness (gain 0.25 .. 1.75 by clip index), so that the whole-tensor norms of a batched
+    call really couple the clips."""
+    gains = 0.25 + 1.5 * (torch.arange(B) % 7).float() / 6.0
+    return synth_wav(B, L, seed) * gains[:, None]
+
+
+def gold_w2v2_batch64(name, tmp, B=64, L=160000, keep=(0, 31, 63)):
+    """BASELINE config 2 at its own shape through the REAL reference lobe: one call on (64, 160000) fp32 (whole-tensor
+    norms over the batch), logits of three clips kept."""
+    cfg = W2V2Config.large()
+    sd = perturb_norm_affines(random_weights(cfg, seed=0))
+    head = random_head(cfg.hidden_size, 20, seed=0)
+    wav = bench_wav(B, L)
+    lobe = _ref_lobe_with(cfg, sd, tmp)
+    lin = rb.reference_linear(cfg.hidden_size, 20)
+    lin.load_state_dict(head)
+    with torch.no_grad():
+        feats = lobe(wav)
+        logits = lin(feats)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), B=B, L=L, wav_seed=1986, weight_seed=0, affine_seed=7, head_seed=0,
+                        clips=np.array(keep), logits=logits[list(keep)].numpy(),
+                        feats_sq_mean=np.float64((feats.double() ** 2).mean().item()))
+    print(name, "logits", tuple(logits.shape), "absmax", float(logits.abs().max()))
+
+
+def gold_fusion_10s(name, B=2, Ta=499, Tv=500, D=1024, d_ffn=3072, nhead=8, row_step=7, col_step=4):
+    """FusionRCA at the frame counts of a 10-s utterance (499 audio / 500 video frames); a strided sample of the output plus
+    a checksum of every row."""
+    sd = random_fusion_weights(D, d_ffn, seed=3)
+    g = torch.Generator().manual_seed(11)
+    a = torch.randn(B, Ta, D, generator=g)
+    v = torch.randn(B, Tv, D, generator=g)
+    ref = rb.reference_fusion(alpha=0.5, nhead=nhead, d_ffn=d_ffn, d_model=D)
+    full = dict(ref.state_dict())
+    full.update(sd)
+    ref.load_state_dict(full, strict=True)
+    with torch.no_grad():
+        out = ref(a, v)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), B=B, Ta=Ta, Tv=Tv, D=D, d_ffn=d_ffn, nhead=nhead, w_seed=3, x_seed=11,
+                        row_step=row_step, col_step=col_step, out_sample=out[:, ::row_step, ::col_step].numpy(),
+                        row_sum=out.double().sum(-1).numpy(), row_sumsq=(out.double() ** 2).sum(-1).numpy())
+    print(name, tuple(out.shape))
+
+
+def gold_bench_shapes():
+    assert rb.available(), "needs /root/reference"
+    torch.set_num_threads(os.cpu_count() or 1)
+    with tempfile.TemporaryDirectory() as tmp:
+        gold_w2v2_batch64("w2v2_large_10s_b64", tmp)
+    gold_fusion_10s("fusion_10s")
+    gold_avhubert_resnet("avhubert_resnet_b1_t500", B=1, T=500, col_step=5)
 
 
 def main():
@@ -248,4 +304,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    if "bench_shapes" in sys.argv[1:]:  # the fixtures at the benchmarked shapes only (round 2); the rest stay as committed
+        gold_bench_shapes()
+    else:
+        main()
+        gold_bench_shapes()

@@ -319,12 +319,23 @@ def encoder(cfg: W2V2Config, sd, h, prefix="model.", taps: Optional[dict] = None
     return h
 
 
+def whole_tensor_stats(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(mean, biased variance) over every element, as `F.layer_norm(x, x.shape)` takes them."""
+    mean = x.mean()
+    return mean, ((x - mean) ** 2).mean()
+
+
 def lobe_forward(cfg: W2V2Config, sd, wav: torch.Tensor, normalize_wav=True, output_norm=True,
-                 prefix="model.", taps: Optional[dict] = None) -> torch.Tensor:
-    """HuggingFaceWav2Vec2.extract_features (huggingface_interface.py:279-298). wav (B,L) -> (B,T,D)."""
+                 prefix="model.", taps: Optional[dict] = None, in_stats=None, out_stats=None) -> torch.Tensor:
+    """HuggingFaceWav2Vec2.extract_features (huggingface_interface.py:279-298). wav (B,L) -> (B,T,D).
+    in_stats / out_stats = (mean, var): use these statistics in the two whole-tensor norms instead of the ones of `wav`
+    itself -- that is how rows of a LARGER reference call are evaluated one clip at a time (amt_logits_of_clips)."""
     x = wav.float()
     if normalize_wav:
-        x = whole_tensor_layer_norm(x)
+        if in_stats is None:
+            x = whole_tensor_layer_norm(x)
+        else:
+            x = (x - in_stats[0]) / torch.sqrt(in_stats[1] + 1e-5)
     h = feature_encoder(cfg, sd, x, prefix, taps).transpose(1, 2)  # HF:1349
     if cfg.feat_proj_layer_norm:  # HF wav2vec2:1352 / hubert HubertFeatureProjection.forward
         h = _ln(sd, h, prefix + "feature_projection.layer_norm.", cfg.layer_norm_eps)
@@ -335,8 +346,33 @@ def lobe_forward(cfg: W2V2Config, sd, wav: torch.Tensor, normalize_wav=True, out
     if taps is not None:
         taps["enc"] = h
     if output_norm:
-        h = whole_tensor_layer_norm(h)
+        if out_stats is None:
+            h = whole_tensor_layer_norm(h)
+        else:
+            h = (h - out_stats[0]) / torch.sqrt(out_stats[1] + 1e-5)
     return h
+
+
+def amt_logits_of_clips(cfg, sd, head_sd, wav: torch.Tensor, clips, stat_clips=None) -> torch.Tensor:
+    """Rows `clips` of amt_logits(cfg, sd, head_sd, wav) -- ONE reference call on the whole batch, whose two whole-tensor
+    norms couple its clips -- evaluated clip by clip so that a 64 x 10 s batch never has to exist in fp32 on the host:
+    the input statistics are taken over all of `wav` (exact), every clip of `stat_clips` (default: all clips = exact) is
+    pushed through the encoder with them, the output statistics are pooled over those clips' features in float64, and the
+    requested clips are normalised and sent through the head.  With stat_clips a SUBSET the output statistics are an
+    estimate; it is exact whenever every row of the final features has the same mean and variance (e.g. gamma = 1, beta = 0
+    in encoder.layer_norm, the HF initialisation)."""
+    clips = list(clips)
+    B = wav.shape[0]
+    stat_clips = list(range(B)) if stat_clips is None else list(stat_clips)
+    in_stats = whole_tensor_stats(wav.float())
+    feats = {}
+    for c in sorted(set(clips) | set(stat_clips)):
+        feats[c] = lobe_forward(cfg, sd, wav[c:c + 1], in_stats=in_stats, output_norm=False)
+    n = sum(feats[c].numel() for c in stat_clips)
+    mean = sum(feats[c].double().sum() for c in stat_clips) / n
+    var = sum(((feats[c].double() - mean) ** 2).sum() for c in stat_clips) / n
+    out_stats = (mean.float(), var.float())
+    return torch.cat([head_forward(head_sd, (feats[c] - out_stats[0]) / torch.sqrt(out_stats[1] + 1e-5)) for c in clips])
 
 
 def head_forward(head_sd, feats: torch.Tensor) -> torch.Tensor:

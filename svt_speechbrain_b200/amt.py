@@ -59,9 +59,12 @@ def frame_info(logits: torch.Tensor, hp: "AMTHparams"):
         check(lib().svt_frame_postproc(ptr(lg), n, lg.shape[1], 2, hp.pitch_octave_num + 1,
                                        2 + hp.pitch_octave_num + 1, hp.pitch_class_num + 1, ptr(octv), ptr(pc),
                                        current_stream_ptr()))
-    on_off = lg[:, :2].cpu()
-    p = torch.sigmoid(on_off)
-    return p[:, 0].contiguous().numpy(), p[:, 1].contiguous().numpy(), octv.cpu().numpy(), pc.cpu().numpy()
+    # one device->host transfer for everything the decoder needs (the int32 ids travel as raw bits in an fp32 tensor)
+    packed = torch.cat([lg[:, :2], octv.view(torch.float32).unsqueeze(1), pc.view(torch.float32).unsqueeze(1)], dim=1).cpu()
+    p = torch.sigmoid(packed[:, :2])
+    ids = packed[:, 2:].contiguous().view(torch.int32)
+    return (p[:, 0].contiguous().numpy(), p[:, 1].contiguous().numpy(), ids[:, 0].contiguous().numpy(),
+            ids[:, 1].contiguous().numpy())
 
 
 def decode_logits(logits: torch.Tensor, hp: "AMTHparams") -> np.ndarray:
@@ -189,24 +192,26 @@ class AMTTranscriber:
 
     @torch.no_grad()
     def transcribe_long(self, wav: torch.Tensor, dur: float = 10.0, overlap: float = 1.0, batch_clips: int = 64,
-                        per_clip_norm: bool = True, group=None) -> np.ndarray:
+                        per_clip_norm: bool = True, group=None, sharded: bool = True) -> np.ndarray:
         """Long-form song (BASELINE config 5): overlapping `dur`-second windows, sharded over the ranks of `group` when
         torch.distributed is initialised (contiguous blocks of windows per rank, no collective inside the forward), frame
         logits gathered in window order, overlaps resolved by `stitch_plan`, one decode of the stitched frames (identical
         on every rank).  overlap = 0 on a song whose length is a multiple of `dur` is `transcribe_song`."""
-        return self.decode(self.long_form_logits(wav, dur, overlap, batch_clips, per_clip_norm, group))
+        return self.decode(self.long_form_logits(wav, dur, overlap, batch_clips, per_clip_norm, group, sharded))
 
     @torch.no_grad()
     def long_form_logits(self, wav: torch.Tensor, dur: float = 10.0, overlap: float = 1.0, batch_clips: int = 64,
-                         per_clip_norm: bool = True, group=None) -> torch.Tensor:
-        """The stitched (n_frames, 20) frame logits behind `transcribe_long` (same on every rank)."""
+                         per_clip_norm: bool = True, group=None, sharded: bool = True) -> torch.Tensor:
+        """The stitched (n_frames, 20) frame logits behind `transcribe_long` (same on every rank).  sharded=False runs every
+        window on this rank even when torch.distributed is initialised (the 1-GPU result, for comparison)."""
         import torch.distributed as dist
         from .parallel import gather_ragged, shard_range
 
         wav = wav.to(self.device, torch.float32).reshape(-1)
         windows = split_song_overlapped(wav.numel(), self.hp.sample_rate, dur, overlap)
-        world = dist.get_world_size(group) if dist.is_initialized() else 1
-        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        use_dist = sharded and dist.is_initialized()
+        world = dist.get_world_size(group) if use_dist else 1
+        rank = dist.get_rank(group) if use_dist else 0
         lo, hi = shard_range(len(windows), rank, world)
         local = self._clip_logits([wav[a:b] for a, b in windows[lo:hi]], batch_clips, per_clip_norm)
         pieces = gather_ragged(local, len(windows), group) if world > 1 else local
@@ -221,7 +226,7 @@ class AMTTranscriber:
         (per-clip normalisation = reference semantics), frames are put back in (song, utterance) order (:88,100) and every
         song is decoded once."""
         hp = self.hp
-        songs = [w.to(self.device, torch.float32).reshape(-1) for w in wavs]
+        songs = [w.to(self.device, torch.float32, non_blocking=True).reshape(-1) for w in wavs]
         jobs = []  # (length, song, utterance index, start, stop)
         for si, w in enumerate(songs):
             for ui, (a, b) in enumerate(split_song(w.numel(), hp, dur)):
@@ -229,11 +234,27 @@ class AMTTranscriber:
         jobs.sort(key=lambda t: (t[0], t[1], t[2]))  # equal lengths become neighbours
         lgs = self._clip_logits([songs[si][a:b] for _, si, _, a, b in jobs], batch_clips, per_clip_norm)
         out = {(si, ui): lg for (_, si, ui, _, _), lg in zip(jobs, lgs)}
-        results = []
+        per_song = []
         for si, w in enumerate(songs):
             n_utt = len(split_song(w.numel(), hp, dur))
-            results.append(self.decode(torch.cat([out[(si, ui)] for ui in range(n_utt)], dim=0)))
-        return results
+            per_song.append(torch.cat([out[(si, ui)] for ui in range(n_utt)], dim=0))
+        return decode_logits_many(per_song, hp)
+
+
+def decode_logits_many(per_song: Sequence[torch.Tensor], hp: "AMTHparams") -> List[np.ndarray]:
+    """Frame logits of several songs -> their note arrays with ONE device pass and ONE device->host transfer for all of
+    them (the per-frame argmax of every song in one svt_frame_postproc launch), instead of three small synchronising
+    copies per song; the host then runs sigmoid + frame2note song by song."""
+    if not per_song:
+        return []
+    counts = [int(t.shape[0]) for t in per_song]
+    p_on, p_off, octv, pc = frame_info(torch.cat(list(per_song), dim=0), hp)
+    res, a = [], 0
+    for n in counts:
+        res.append(decode_arrays(p_on[a:a + n], p_off[a:a + n], octv[a:a + n], pc[a:a + n], hp.onset_threshold,
+                                 hp.offset_threshold, 1.0 / hp.frame_rate))
+        a += n
+    return res
 
 
 class AVTranscriber:

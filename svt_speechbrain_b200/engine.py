@@ -108,7 +108,10 @@ class EncoderEngine:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def forward(self, wav: torch.Tensor, want_feats: bool = True, want_logits: bool = False):
+    def forward(self, wav: torch.Tensor, want_feats: bool = True, want_logits: bool = False,
+                logits_out: Optional[torch.Tensor] = None):
+        """logits_out: optional pre-allocated (B, T, n_out) fp32 CUDA tensor to write the logits into (serving loops that
+        hand the buffer to an asynchronous collective)."""
         require_cuda(wav, "EncoderEngine.forward")
         if wav.dim() != 2:
             raise ValueError(f"expected wav of shape (batch, samples), got {tuple(wav.shape)}")
@@ -123,7 +126,13 @@ class EncoderEngine:
         if want_logits:
             if self.n_out <= 0:
                 raise RuntimeError("no head set")
-            logits = torch.empty(B, T, self.n_out, dtype=torch.float32, device=wav.device)
+            if logits_out is not None:
+                if (tuple(logits_out.shape) != (B, T, self.n_out) or logits_out.dtype != torch.float32 or
+                        not logits_out.is_contiguous() or logits_out.device != wav.device):
+                    raise ValueError(f"logits_out must be a contiguous fp32 tensor of shape {(B, T, self.n_out)} on {wav.device}")
+                logits = logits_out
+            else:
+                logits = torch.empty(B, T, self.n_out, dtype=torch.float32, device=wav.device)
         with torch.cuda.device(wav.device):
             check(lib().svt_encoder_forward(self._h, ptr(wav), B, L, ptr(ws), ws.numel(), ptr(feats), ptr(logits),
                                             current_stream_ptr()))

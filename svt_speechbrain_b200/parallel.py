@@ -21,18 +21,80 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
 
 def gather_logits(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
     """All-gather per-rank logits (n_local, T, C) into (n_total, T, C) in clip order on every rank.
-    Ranks may own different clip counts; blocks are padded to the largest one for the collective."""
+    Equal blocks (n_total % world == 0) go through one `all_gather_into_tensor` straight into the result; ragged blocks
+    are padded to the largest one for the collective."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return local
-    rank = dist.get_rank(group)
     counts = [shard_range(n_total, r, world) for r in range(world)]
+    if n_total % world == 0:
+        if local.shape[0] != n_total // world:
+            raise ValueError(f"rank owns {n_total // world} clips but passed {local.shape[0]}")
+        out = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     n_max = max(b - a for a, b in counts)
     pad = torch.zeros((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     bufs: List[torch.Tensor] = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad, group=group)
     return torch.cat([bufs[r][: counts[r][1] - counts[r][0]] for r in range(world)], dim=0)
+
+
+class LogitsGatherer:
+    """Serving-loop gather of equal per-rank logits blocks that never stalls the next forward.
+
+    The reference's multi-GPU inference (nn.DataParallel, speechbrain/core.py:1164-1169) gathers the outputs of every step
+    on the host thread, a global rendezvous per step.  Here step k's `ncclAllGather` is issued asynchronously (c10d runs it
+    on its own stream, ordered after the producing kernels by an event) into one of `depth` pre-allocated
+    (world * n_local, T, C) buffers, and the compute stream only waits for it when the result is consumed or when the
+    buffer comes round again -- so step k + 1's forward is queued right behind step k's and a rank that is momentarily
+    slower delays nobody until `depth` steps later.
+
+        g = LogitsGatherer((B, T, 20), depth=2, device=dev)
+        for k, wav in enumerate(batches):
+            eng.forward(wav, want_feats=False, want_logits=True, logits_out=g.local(k))
+            g.submit(k)                      # asynchronous all-gather of slot k % depth
+            if k >= 1: use(g.result(k - 1))  # (world * B, T, 20), blocks the CURRENT STREAM only, not the host
+    """
+
+    def __init__(self, local_shape, depth: int = 2, device=None, dtype=torch.float32, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.depth = depth
+        self._local = [torch.empty(tuple(local_shape), dtype=dtype, device=device) for _ in range(depth)]
+        self._out = [torch.empty((self.world * local_shape[0],) + tuple(local_shape[1:]), dtype=dtype, device=device)
+                     for _ in range(depth)] if self.world > 1 else self._local
+        self._work = [None] * depth
+        self._step = [-1] * depth
+
+    def local(self, k: int) -> torch.Tensor:
+        """The buffer step k's forward writes its logits into.  Re-using a slot first drains the gather that read it."""
+        s = k % self.depth
+        self._drain(s)
+        return self._local[s]
+
+    def submit(self, k: int) -> None:
+        s = k % self.depth
+        self._step[s] = k
+        if self.world > 1:
+            self._work[s] = dist.all_gather_into_tensor(self._out[s], self._local[s], group=self.group, async_op=True)
+
+    def result(self, k: int) -> torch.Tensor:
+        s = k % self.depth
+        if self._step[s] != k:
+            raise ValueError(f"step {k} is not in flight (slot holds step {self._step[s]})")
+        self._drain(s)
+        return self._out[s]
+
+    def _drain(self, s: int) -> None:
+        if self._work[s] is not None:
+            self._work[s].wait()  # stream-level wait for NCCL; host-blocking for gloo (CPU tests)
+            self._work[s] = None
+
+    def finish(self) -> None:
+        for s in range(self.depth):
+            self._drain(s)
 
 
 def gather_notes(local_notes: List, group=None) -> List:

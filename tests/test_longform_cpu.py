@@ -69,3 +69,22 @@ def test_gather_ragged_two_ranks(n_total):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res)
+
+
+def test_tail_shorter_than_one_frame_is_merged_into_the_last_window():
+    """A song that ends less than one receptive field after a window boundary: the remainder joins the previous window (as
+    the reference's last utterance takes the remainder, prepare_benchmarks.py:124-127) instead of becoming a window without
+    frames, which one rank alone would have had to reject."""
+    w = split_song_overlapped(320100, 16000, 10.0, 0.0)
+    assert w == [(0, 160000), (160000, 320100)]
+    w = split_song_overlapped(16000 * 19 + 100, 16000, 10.0, 1.0)   # hop 9 s: third window would start at 18 s with 1.006 s left
+    assert all(b - a >= FRAME_FIELD for a, b in w) and w[-1][1] == 16000 * 19 + 100
+    n = 16000 * 18 + 200                                            # ... and here with 200 samples left
+    w = split_song_overlapped(n, 16000, 10.0, 1.0)
+    assert w == [(0, 160000), (144000, n)]
+    plan = stitch_plan(w)
+    g = 0
+    for (a, b), (lo, hi) in zip(w, plan):
+        assert a // FRAME_HOP + lo == g
+        g = a // FRAME_HOP + hi
+    assert g == (n - FRAME_FIELD) // FRAME_HOP + 1

@@ -108,3 +108,67 @@ def test_avhubert_tiny_forward_shapes_and_key_translation():
     with torch.no_grad():
         y = av.lobe_forward(cfg, sd, video)
     assert y.shape == (1, 5, 128) and abs(float(y.mean())) < 1e-4 and abs(float(y.var(unbiased=False)) - 1.0) < 1e-3
+
+
+def test_clip_by_clip_restatement_of_a_batched_call_equals_the_batched_oracle():
+    """amt_logits_of_clips (used to check 64 x 10 s batches without materialising them in fp32 on the host) against
+    amt_logits on the same batch, with LayerNorm affines perturbed so the whole-tensor statistics are not trivial."""
+    import torch
+    from oracle import make_golden as mg
+    from oracle import wav2vec2_oracle as wo
+
+    cfg = wo.W2V2Config(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                        feat_extract_norm="layer", conv_bias=True, do_stable_layer_norm=True, num_conv_pos_embeddings=16,
+                        num_conv_pos_embedding_groups=2)
+    sd = mg.perturb_norm_affines(wo.random_weights(cfg, seed=0), seed=7)
+    head = wo.random_head(cfg.hidden_size, 20, seed=0)
+    wav = mg.synth_wav(4, 6000, seed=3) * torch.tensor([[0.3], [1.0], [2.0], [0.7]])
+    with torch.no_grad():
+        full = wo.amt_logits(cfg, sd, head, wav)
+        part = wo.amt_logits_of_clips(cfg, sd, head, wav, [0, 3])
+        single = wo.amt_logits(cfg, sd, head, wav[3:4])
+    assert part.shape == (2,) + full.shape[1:]
+    assert float((part - full[[0, 3]]).abs().max()) < 2e-4
+    assert float((single[0] - full[3]).abs().max()) > 1e-2  # the batch coupling is real
+
+
+def test_oracle_vs_reference_at_benchmark_shapes(gold_dir):
+    """The round-2 fixtures made by the REAL reference at the benchmarked shapes: one (64, 160000) call of the lobe (three
+    clips kept), FusionRCA at 499 / 500 frames, ResEncoder at 500 frames."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import avhubert_oracle as av
+    from oracle import fusion_oracle as fo
+    from oracle import make_golden as mg
+    from oracle import wav2vec2_oracle as wo
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    # ---- config 2's own shape.  The output statistics are pooled over the three kept clips instead of all 64 (an estimate
+    # from 1.5 M of the 32.7 M feature values; running all 64 clips is the GPU test's job), hence the 2e-3 bound.
+    g = np.load(os.path.join(gold_dir, "w2v2_large_10s_b64.npz"))
+    cfg = wo.W2V2Config.large()
+    sd = mg.perturb_norm_affines(wo.random_weights(cfg, seed=int(g["weight_seed"])), seed=int(g["affine_seed"]))
+    head = wo.random_head(cfg.hidden_size, 20, seed=int(g["head_seed"]))
+    wav = mg.bench_wav(int(g["B"]), int(g["L"]), seed=int(g["wav_seed"]))
+    keep = [int(c) for c in g["clips"]]
+    with torch.no_grad():
+        got = wo.amt_logits_of_clips(cfg, sd, head, wav, clips=keep, stat_clips=keep)
+    assert float((got - torch.from_numpy(g["logits"])).abs().max()) < 2e-3
+    # ---- FusionRCA, 10-s utterance
+    g = np.load(os.path.join(gold_dir, "fusion_10s.npz"))
+    fsd = mg.random_fusion_weights(int(g["D"]), int(g["d_ffn"]), seed=int(g["w_seed"]))
+    gen = torch.Generator().manual_seed(int(g["x_seed"]))
+    a = torch.randn(int(g["B"]), int(g["Ta"]), int(g["D"]), generator=gen)
+    v = torch.randn(int(g["B"]), int(g["Tv"]), int(g["D"]), generator=gen)
+    with torch.no_grad():
+        out = fo.fusion_forward(fsd, a, v, nhead=int(g["nhead"]))
+    assert float((out[:, ::int(g["row_step"]), ::int(g["col_step"])] - torch.from_numpy(g["out_sample"])).abs().max()) < 1e-4
+    assert np.abs((out.double() ** 2).sum(-1).numpy() - g["row_sumsq"]).max() < 1e-2
+    # ---- lip-video ResNet, 500 frames
+    d = np.load(os.path.join(gold_dir, "avhubert_resnet_b1_t500.npz"))
+    sd0 = av.random_weights(av.AVHubertConfig(encoder_layers=0), seed=int(d["weight_seed"]))
+    video = torch.randn(int(d["B"]), 1, int(d["T"]), 88, 88, generator=torch.Generator().manual_seed(int(d["video_seed"])))
+    with torch.no_grad():
+        res = av.res_encoder(sd0, video, "model.feature_extractor_video.resnet.")
+    assert float((res[:, ::int(d["col_step"])] - torch.from_numpy(d["out"])).abs().max()) < 2e-4

@@ -43,3 +43,45 @@ def test_gather_logits_uneven_shards():
     for rank, ok, pitches in res:
         assert ok, rank
         assert pitches == [60 + i for i in range(n_total)]
+
+
+def _gatherer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from svt_speechbrain_b200.parallel import LogitsGatherer, gather_logits
+
+    B, T, C, steps = 3, 5, 20, 5
+    g = LogitsGatherer((B, T, C), depth=2, device="cpu")
+    ok = True
+    for k in range(steps):
+        g.local(k).copy_(torch.full((B, T, C), float(100 * k + rank)))   # what the forward of step k would write
+        g.submit(k)
+        if k >= 1:  # consume one step behind: step k - 1's gather completes while step k is being produced
+            got = g.result(k - 1)
+            want = torch.cat([torch.full((B, T, C), float(100 * (k - 1) + r)) for r in range(world)])
+            ok = ok and torch.equal(got, want)
+    ok = ok and torch.equal(g.result(steps - 1)[B:], torch.full((B, T, C), float(100 * (steps - 1) + 1)))
+    g.finish()
+    try:
+        g.result(0)  # its slot was reused by steps 2 and 4
+        ok = False
+    except ValueError:
+        pass
+    even = gather_logits(torch.full((2, T, C), float(rank)), 4)  # equal blocks: the all_gather_into_tensor path
+    ok = ok and torch.equal(even, torch.cat([torch.zeros(2, T, C), torch.ones(2, T, C)]))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_double_buffered_gatherer_and_even_gather():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gatherer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res

@@ -8,6 +8,11 @@ Workload (`config.workload`): BASELINE config 2 -- wav2vec2-large (random init, 
 Linear(1024->20), 64 synthetic 10-s 16 kHz clips per GPU per step, bf16 storage / fp32 accumulate.  With N > 1
 every rank runs its own 64 clips (weak scaling; N = 8 is BASELINE config 3's 512 clips) and the frame logits
 are all-gathered over NCCL inside the timed region.  A "step" = wav (resident in HBM) -> frame logits.
+
+Beside the headline the line carries: `parity` (the LAST TIMED STEP's logits of three clips against the fp32 oracle),
+`e2e` (host buffers in and out; at N > 1 including the gather), `e2e_notes` (host wav -> host notes through the evaluation
+driver, where the CPU arm ends), `multi_gpu` (per-rank ms/step and a with/without-gather A/B), `aux.av` (BASELINE config 4)
+and `aux.longform` (config 5), `roofline`, `cpu_baseline` (oracle port at batch 1).
 """
 from __future__ import annotations
 
@@ -171,15 +176,32 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+GFLOP_PER_AUDIO_SEC_AV = 107.1  # config 4: (383.86 audio + 653.7 video + 33.4 fusion) GFLOP per 10-s clip
+PARITY_CLIPS = (0, 31, 63)
+
+
+def _lobe_dir(cfg):
+    """Offline model directory (config + feature-extractor config) for the reference-shaped lobe."""
+    import tempfile
+    from transformers import Wav2Vec2Config, Wav2Vec2FeatureExtractor
+
+    d = os.path.join(tempfile.mkdtemp(), "wav2vec2-bench")
+    os.makedirs(d)
+    Wav2Vec2Config(**cfg.hf_kwargs()).save_pretrained(d)
+    Wav2Vec2FeatureExtractor(feature_size=1, sampling_rate=16000, padding_value=0.0, do_normalize=True,
+                             return_attention_mask=True).save_pretrained(d)
+    return d
+
+
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
 
     import svt_speechbrain_b200 as svt
-    from oracle import wav2vec2_oracle as wo  # weights-by-seed helper only (HF init); not on the timed path
+    from oracle import wav2vec2_oracle as wo  # weights-by-seed helper (HF init) + the parity CHECK after the timed region
     from svt_speechbrain_b200._lib import lib
-    from svt_speechbrain_b200.engine import EncoderEngine, encoder_config_from_hf
-    from svt_speechbrain_b200.parallel import gather_logits
+    from svt_speechbrain_b200.parallel import LogitsGatherer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -191,89 +213,191 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    # the reference-shaped modules (what a recipe's YAML instantiates), random init as BASELINE.json names it
     B, L = args.batch, CLIP_SECONDS * SAMPLE_RATE
     cfg = wo.W2V2Config.large()
-    from transformers import Wav2Vec2Config
-    hf_cfg = Wav2Vec2Config(**cfg.hf_kwargs())
-    eng = EncoderEngine(encoder_config_from_hf(hf_cfg, True, True), dev)
+    d = _lobe_dir(cfg)
+    lobe = svt.HuggingFaceWav2Vec2(source=d, save_path=d, pretrain=False, output_norm=True, freeze=True)
     sd = wo.random_weights(cfg, seed=0)
+    lobe.load_state_dict(sd, strict=True)
     head = wo.random_head(cfg.hidden_size, 20, seed=0)
-    eng.load(sd, head["w.weight"], head["w.bias"])
-    del sd
+    lin = svt.Linear(n_neurons=20, input_size=cfg.hidden_size)
+    lin.load_state_dict(head)
+    hp = svt.AMTHparams(dur_threshold=float(CLIP_SECONDS))
+    tr = svt.AMTTranscriber(lobe.to(dev), lin.to(dev), hp, device=dev)
+    eng = tr._engine()
     T = eng.num_frames(L)
 
     # 4 rotating input batches (4 x 41 MB > 126 MB L2): inputs are never L2-resident; the step itself streams
     # > 3 GB of activations through HBM, so nothing survives in L2 from one step to the next either.
     gen = torch.Generator(device=dev).manual_seed(1986 + rank)
     wavs = [torch.randn(B, L, device=dev, generator=gen) for _ in range(4)]
+    gat = LogitsGatherer((B, T, 20), depth=2, device=dev)
 
-    def step(i):
-        _, lg = eng.forward(wavs[i % 4], want_feats=False, want_logits=True)
-        if world > 1:
-            lg = gather_logits(lg, B * world)
-        return lg
+    def step(i, gather=True):
+        # forward of step i writes into slot i % 2; its all-gather is asynchronous (own NCCL stream), so the forward of
+        # step i + 1 is queued behind this one without waiting for the collective
+        eng.forward(wavs[i % 4], want_feats=False, want_logits=True, logits_out=gat.local(i))
+        if gather:
+            gat.submit(i)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(n, gather=True):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.time()
+        e0.record()
+        for i in range(n):
+            step(i, gather)
+        gat.finish()  # the last gathers are part of the timed work
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), t0, time.time()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x), [float(x)]
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        allv = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allv, t)
+        vals = [float(v.item()) for v in allv]
+        return max(vals), vals
+
     for i in range(args.warmup):
         step(i)
+    gat.finish()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
     n0 = lib().svt_debug_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_wall0 = time.time()
-    e0.record()
-    for i in range(args.steps):
-        out = step(i)
-    e1.record()
-    barrier()
-    t_wall1 = time.time()
-    ms_total = e0.elapsed_time(e1)
+    ms_total, t_wall0, t_wall1 = timed(args.steps)
     launches = lib().svt_debug_launch_count() - n0
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_total, per_rank_ms = max_over_ranks(ms_total)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = world * B * CLIP_SECONDS / (ms_per_step * 1e-3)
+    last_slot = (args.steps - 1) % gat.depth
+    last_logits = gat._local[last_slot].clone()       # this rank's logits of the last timed step
+    last_wav = wavs[(args.steps - 1) % 4]
+    multi = None
+    if world > 1:
+        ms_ng, _, _ = timed(args.steps, gather=False)
+        ms_ng, per_rank_ng = max_over_ranks(ms_ng)
+        multi = {"per_rank_ms_per_step": [v / args.steps for v in per_rank_ms],
+                 "without_gather": {"ms_per_step": ms_ng / args.steps, "per_rank_ms_per_step": [v / args.steps for v in per_rank_ng]},
+                 "gather": "ncclAllGather (all_gather_into_tensor) of the (B, T, 20) fp32 logits into pre-allocated double-buffered "
+                           "(N*B, T, 20) tensors, asynchronous on the NCCL stream, drained when the slot is reused / at the end"}
 
-    # ---- end to end through the C-ABI host-buffer pipeline (svt_pipeline_*): every step copies its own pinned host wav
-    # to the device and its logits back to pinned host memory; two batches are in flight, so the copy of step k + 1
-    # runs under the forward of step k.  Host clock from the first submit to the last completed result.
+    # ---- parity of the timed shape, outside the timed region: the last timed step's logits of three clips against the fp32
+    # oracle evaluating ONE batched reference call clip by clip (input statistics over the whole batch; output statistics
+    # pooled over the checked clips, exact here because encoder.layer_norm has gamma = 1, beta = 0 at HF init -> every row
+    # of the final features has mean 0 and the same variance).
+    parity = None
+    if rank == 0 and not args.no_parity:
+        clips = [c for c in PARITY_CLIPS if c < B]
+        with torch.no_grad():
+            ref = wo.amt_logits_of_clips(cfg, sd, head, last_wav.cpu(), clips=clips, stat_clips=clips)
+        got = last_logits[clips].cpu()
+        parity = {"rel_l2": float((got - ref).norm() / ref.norm()), "max_abs": float((got - ref).abs().max()),
+                  "clips": clips, "shape": [B, L], "tolerance": {"rel_l2": 2e-2, "max_abs": 0.1},
+                  "against": "fp32 CPU oracle (oracle/wav2vec2_oracle.py, pinned to the reference's own output at this shape by "
+                             "tests/golden/w2v2_large_10s_b64.npz), logits of the LAST TIMED STEP"}
+        parity["ok"] = bool(parity["rel_l2"] <= 2e-2 and parity["max_abs"] <= 0.1)
+        del ref, got
+
+    # ---- e2e #1 (N = 1): the C-ABI host-buffer pipeline (svt_pipeline_*): every step copies its own pinned host wav to the
+    # device and its logits back to pinned host memory; two batches in flight, the copy of step k + 1 runs under the
+    # forward of step k.  N > 1: the same with the all-gather of the step's logits INSIDE the loop -- pinned host wav ->
+    # H2D (copy stream) -> forward -> async all-gather -> D2H of the gathered (N*B, T, 20) logits on every rank.
     wav_host = [torch.randn(B, L, generator=torch.Generator().manual_seed(7 + i)).pin_memory() for i in range(2)]
-    logits_host = [torch.empty(B, T, 20).pin_memory() for _ in range(2)]
-    pipe = eng.pipeline(B, L, depth=2)
+    n_e2e = max(2, args.steps)
+    if world == 1:
+        logits_host = [torch.empty(B, T, 20).pin_memory() for _ in range(2)]
+        pipe = eng.pipeline(B, L, depth=2)
 
-    def run_pipe(n):
-        pending = []
-        for i in range(n):
-            pending.append(pipe.submit(wav_host[i % 2], logits_host[i % 2]))
-            if len(pending) == 2:
-                pipe.wait(pending.pop(0))  # result i - 1 is on the host (a consumer would read logits_host[(i - 1) % 2] here)
-        for t in pending:
-            pipe.wait(t)
+        def run_pipe(n):
+            pending = []
+            for i in range(n):
+                pending.append(pipe.submit(wav_host[i % 2], logits_host[i % 2]))
+                if len(pending) == 2:
+                    pipe.wait(pending.pop(0))  # result i - 1 is on the host (a consumer would read logits_host[(i - 1) % 2])
+            for t in pending:
+                pipe.wait(t)
 
-    run_pipe(max(2, args.warmup // 2))
+        run_pipe(max(2, args.warmup // 2))
+        barrier()
+        t0 = time.perf_counter()
+        run_pipe(n_e2e)
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+        pipe.close()
+        del pipe
+        e2e_api = "svt_pipeline_submit / svt_pipeline_wait, depth 2 (pinned host wav -> H2D -> forward -> D2H pinned host logits, every step)"
+        d2h = B * T * 20 * 4
+    else:
+        gathered_host = [torch.empty(world * B, T, 20).pin_memory() for _ in range(2)]
+        wav_dev = [torch.empty(B, L, device=dev) for _ in range(2)]
+        copy_s = torch.cuda.Stream(device=dev)
+        main_s = torch.cuda.current_stream(dev)
+        h2d_done = [torch.cuda.Event() for _ in range(2)]
+        fwd_done = [torch.cuda.Event() for _ in range(2)]
+        d2h_done = [torch.cuda.Event() for _ in range(2)]
+
+        def run_pipe(n):
+            for i in range(n + 1):
+                if i < n:
+                    s = i % 2
+                    with torch.cuda.stream(copy_s):
+                        if i >= 2:
+                            copy_s.wait_event(fwd_done[s])     # the forward that read this staging slot has finished
+                        wav_dev[s].copy_(wav_host[s], non_blocking=True)
+                        h2d_done[s].record(copy_s)
+                    main_s.wait_event(h2d_done[s])
+                    eng.forward(wav_dev[s], want_feats=False, want_logits=True, logits_out=gat.local(i))
+                    fwd_done[s].record(main_s)
+                    gat.submit(i)
+                if i >= 1:                                     # consume step i - 1: gathered logits -> pinned host
+                    k = i - 1
+                    if k >= 2:
+                        d2h_done[k % 2].synchronize()          # the host buffer's previous result has been read out
+                    gathered_host[k % 2].copy_(gat.result(k), non_blocking=True)
+                    d2h_done[k % 2].record(main_s)
+            gat.finish()
+            torch.cuda.synchronize()
+
+        run_pipe(max(2, args.warmup // 2))
+        barrier()
+        t0 = time.perf_counter()
+        run_pipe(n_e2e)
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+        e2e_api = ("pinned host wav -> H2D (copy stream) -> EncoderEngine.forward -> asynchronous NCCL all-gather of the logits -> "
+                   "D2H of the gathered (N*B, T, 20) logits to pinned host memory on every rank, double-buffered")
+        d2h = world * B * T * 20 * 4
+    e2e_s, _ = max_over_ranks(e2e_s)
+    e2e_value = world * B * CLIP_SECONDS / e2e_s
+
+    # ---- e2e #2, where the CPU arm ends: wav on the HOST -> notes on the HOST through AMTTranscriber.transcribe_songs (the
+    # evaluation driver: H2D, batched per-clip-norm forward, one argmax pass + one D2H, host sigmoid + frame2note per song).
+    songs_host = [wav_host[0][c] for c in range(B)]
+    tr.transcribe_songs(songs_host[: min(B, 8)], dur=float(CLIP_SECONDS), batch_clips=B)
+    n_notes_runs = max(2, min(args.steps, 5))
     barrier()
     t0 = time.perf_counter()
-    n_e2e = max(2, args.steps)
-    run_pipe(n_e2e)
+    for _ in range(n_notes_runs):
+        notes = tr.transcribe_songs(songs_host, dur=float(CLIP_SECONDS), batch_clips=B)
     barrier()
-    e2e_s = (time.perf_counter() - t0) / n_e2e
-    pipe.close()
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * B * CLIP_SECONDS / e2e_s
+    notes_s, _ = max_over_ranks((time.perf_counter() - t0) / n_notes_runs)
+    e2e_notes = {"value": world * B * CLIP_SECONDS / notes_s, "unit": "audio-sec/sec", "ms_per_batch": notes_s * 1e3,
+                 "notes_per_batch": int(sum(len(n) for n in notes)),
+                 "api": f"AMTTranscriber.transcribe_songs({B} host songs of 10 s, dur=10, per-clip norm = the reference's batch-size-1 "
+                        "evaluation) -> note arrays on the host; not pipelined across calls"}
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM, here the FFN-1 shape of the step) timed alone
     peaks = _peaks()
@@ -311,10 +435,25 @@ def run_ours(args):
                                   "profiles/r1_ncu_full_v3_summary.csv (algorithmic: A 65.5 MB + W 8.4 MB + row statistics 2 MB + out 262.1 MB)",
                 "peak_source": peaks["src"] + " burst (kernel timed alone)", "us_per_launch": t_ms * 1e3,
                 "whole_step": {"achieved": step_tf, "peak": peaks["bf16_sustained"], "frac": step_tf / peaks["bf16_sustained"],
+                               "frac_of_burst": step_tf / peaks["bf16"],
                                "peak_source": peaks["src"] + " sustained", "note": "38.386 GFLOP per audio-second (BASELINE.md section 3)"}}
+        del a, w, o, flush, stats
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_throughput(3, 1)
             cpu_base = {k: v for k, v in cb.items() if k != "s_per_clip"}
+
+    # ---- aux: the two other measured configurations of BASELINE.json, a few steps each
+    aux = None
+    if not args.no_aux:
+        aux = {}
+        try:
+            aux["av"] = _aux_av(args, tr, lobe, lin, dev, world, rank, barrier, max_over_ranks, peaks, sd)
+        except Exception as e:  # an aux leg must never take the headline line down with it
+            aux["av"] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            aux["longform"] = _aux_longform(args, tr, dev, world, rank, barrier, max_over_ranks)
+        except Exception as e:
+            aux["longform"] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         line = {
@@ -323,14 +462,108 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(B, world, T),
             "e2e": {"value": e2e_value, "unit": "audio-sec/sec", "h2d_bytes_per_step": B * L * 4,
-                    "d2h_bytes_per_step": B * T * 20 * 4, "api": "svt_pipeline_submit / svt_pipeline_wait, depth 2 (pinned host wav -> H2D -> forward -> D2H pinned host logits, every step)"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+                    "d2h_bytes_per_step": d2h, "api": e2e_api, "gather_included": world > 1},
+            "e2e_notes": e2e_notes,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "parity": parity,
         }
+        if multi is not None:
+            line["multi_gpu"] = multi
+        if aux is not None:
+            line["aux"] = aux
         if cpu_base is not None:
+            cpu_base["note"] = "oracle PORT at BATCH 1 (one 10-s clip per pass, the reference's own evaluation batch size), not the 64-clip batch"
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _aux_av(args, tr, lobe, lin, dev, world, rank, barrier, max_over_ranks, peaks, audio_sd):
+    """BASELINE config 4 (N20EMv2 audio-visual AMT, batch 32 on 8 GPUs = 4 clips per GPU): wav2vec2-large + AV-HuBERT-large
+    video stream + FusionRCA + head through AVTranscriber.logits, logits all-gathered when N > 1.  The video stream's
+    transformer body is parity-unpinned (fairseq cannot be imported)."""
+    import torch
+
+    import svt_speechbrain_b200 as svt
+    from oracle import avhubert_oracle as av   # seeded AV-HuBERT-large-shaped weights only
+    from oracle import make_golden as mg       # seeded FusionRCA weights only
+    from svt_speechbrain_b200.fairseq_interface import FairseqAVHubertPretrain
+    from svt_speechbrain_b200.parallel import gather_logits
+
+    Bc = args.av_clips
+    vcfg = av.AVHubertConfig()
+    mc = dict(encoder_embed_dim=vcfg.encoder_embed_dim, encoder_layers=vcfg.encoder_layers,
+              encoder_attention_heads=vcfg.encoder_attention_heads, encoder_ffn_embed_dim=vcfg.encoder_ffn_embed_dim,
+              conv_pos=vcfg.conv_pos, conv_pos_groups=vcfg.conv_pos_groups)
+    vlobe = FairseqAVHubertPretrain(None, None, output_norm=True, pretrain=False, model_config=mc)
+    vsd = av.random_weights(vcfg, seed=0, hf_sd=audio_sd)  # same transformer-body init as the audio model (identical geometry)
+    own = vlobe.state_dict()
+    vlobe.load_state_dict({k: vsd[k] for k in own if k in vsd}, strict=False)
+    del vsd
+    fus = svt.FusionRCA()
+    full = dict(fus.state_dict())
+    full.update(mg.random_fusion_weights(1024, 3072, seed=3))
+    fus.load_state_dict(full, strict=True)
+    avt = svt.AVTranscriber(lobe, vlobe.to(dev), fus.to(dev), lin, tr.hp, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(4 + rank)
+    wav = torch.randn(Bc, CLIP_SECONDS * SAMPLE_RATE, device=dev, generator=gen)
+    video = torch.randn(Bc, 1, 50 * CLIP_SECONDS, 88, 88, device=dev, generator=gen)
+
+    def step():
+        return gather_logits(avt.logits(wav, video), Bc * world)
+
+    for _ in range(3):
+        out = step()
+    n = max(3, min(args.steps, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(n):
+        out = step()
+    e1.record()
+    barrier()
+    ms, _ = max_over_ranks(e0.elapsed_time(e1) / n)
+    asps = world * Bc * CLIP_SECONDS / (ms * 1e-3)
+    tf = GFLOP_PER_AUDIO_SEC_AV * 1e9 * (asps / world) / 1e12
+    notes = avt.decode(out[0])
+    return {"workload": f"BASELINE config 4: wav2vec2-large + AV-HuBERT-large video stream (500 lip frames of 88x88) + FusionRCA + head, "
+                        f"{Bc} x 10-s clips per GPU ({Bc * world} per step), logits all-gathered when N>1",
+            "ms_per_step": ms, "audio_s_per_s": asps, "steps": n,
+            "frac_of_peak": tf / peaks["bf16"], "tflops_per_gpu": tf,
+            "gflop_per_audio_s": GFLOP_PER_AUDIO_SEC_AV, "finite": bool(torch.isfinite(out).all()), "notes_clip0": int(len(notes)),
+            "parity_note": "video transformer body parity-unpinned (fairseq absent); ResNet front end pinned at 500 frames, fusion at 499/500"}
+
+
+def _aux_longform(args, tr, dev, world, rank, barrier, max_over_ranks):
+    """BASELINE config 5: one 5-minute song, overlapping 10-s windows sharded over the N ranks, ragged NCCL gather of the
+    frame logits, stitched, decoded once; compared with all windows on one GPU."""
+    import numpy as np
+    import torch
+
+    wav = (torch.randn(SAMPLE_RATE * 300 + 4321, generator=torch.Generator().manual_seed(0)) * 0.1).pin_memory()
+
+    def run():
+        return tr.transcribe_long(wav, dur=10.0, overlap=1.0)
+
+    for _ in range(2):
+        notes = run()
+    n = 3
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        notes = run()
+    barrier()
+    wall, _ = max_over_ranks((time.perf_counter() - t0) / n)
+    out = {"workload": "BASELINE config 5: 300.27-s song, 10-s windows with 1-s overlap (34 windows) sharded over the ranks, "
+                       "stitched frame logits, one decode; host wav -> host notes",
+           "wall_s": wall, "audio_s_per_s": wav.numel() / SAMPLE_RATE / wall, "notes": int(len(notes)), "equal_to_1gpu": None}
+    if world > 1:
+        sharded = tr.long_form_logits(wav, dur=10.0, overlap=1.0)
+        single = tr.long_form_logits(wav, dur=10.0, overlap=1.0, sharded=False)
+        out["equal_to_1gpu"] = bool(torch.equal(sharded, single))
+        out["max_abs_vs_1gpu"] = float((sharded - single).abs().max())
+        out["notes_equal_to_1gpu"] = bool(np.array_equal(tr.decode(sharded), tr.decode(single)))
+    return out
 
 
 def main():
@@ -341,6 +574,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the config 4 (audio-visual) and config 5 (long-form) legs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the last timed step's logits")
+    ap.add_argument("--av-clips", type=int, default=4, help="clips per GPU of the audio-visual leg (config 4: 32 / 8 GPUs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -142,7 +142,7 @@ def lobe_forward(cfg: AVHubertConfig, sd, video: torch.Tensor, input_norm: bool 
     return out
 
 
-def random_weights(cfg: AVHubertConfig, seed: int = 0, prefix: str = "model.") -> Dict[str, torch.Tensor]:
+def random_weights(cfg: AVHubertConfig, seed: int = 0, prefix: str = "model.", hf_sd=None) -> Dict[str, torch.Tensor]:
     """Seeded random weights with the reference's shapes and init scales (resnet.py:93-100 conv init; BN with
     non-trivial running statistics and affines so that the folding is exercised; PReLU slopes around 0.25;
     transformer weights via HF's `_init_weights` renamed to fairseq keys)."""
@@ -186,7 +186,8 @@ def random_weights(cfg: AVHubertConfig, seed: int = 0, prefix: str = "model.") -
     sd[prefix + "post_extract_proj.weight"] = rn(D, 2 * D, std=1.0 / math.sqrt(2 * D))
     sd[prefix + "post_extract_proj.bias"] = 0.05 * rn(D)
     # transformer body: HF init of the equivalent stable-LN encoder, keys renamed to fairseq
-    hf = wo.random_weights(cfg.w2v2(), seed=seed)
+    # (hf_sd: an already built wo.random_weights(cfg.w2v2(), seed) state dict, to skip building the HF model twice)
+    hf = wo.random_weights(cfg.w2v2(), seed=seed) if hf_sd is None else hf_sd
     for k, v in hf.items():
         if not k.startswith("model.encoder."):
             continue

@@ -416,6 +416,8 @@ def run_ours(args):
         o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         times = []
+        torch.cuda.synchronize()
+        time.sleep(2.0)  # "kernel timed alone": let the power / thermal state of the legs above settle (burst-peak conditions)
         for it in range(3 + 10):
             flush.zero_()  # evict L2 between timed launches
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -51,20 +51,7 @@ def frame_info(logits: torch.Tensor, hp: "AMTHparams"):
     """(n_frames, 20) CUDA logits -> host arrays (p_on f32, p_off f32, octave i32, pitch_class i32)
     (train_audio_ssl.py:93-100).  argmax runs on the device (first max wins); the two sigmoids are taken on the HOST
     with torch so the probabilities are bit-identical to the CPU reference that frame2note's `==` / `>=` tests see."""
-    lg = logits.reshape(-1, logits.shape[-1]).contiguous()
-    n = lg.shape[0]
-    octv = torch.empty(n, dtype=torch.int32, device=lg.device)
-    pc = torch.empty(n, dtype=torch.int32, device=lg.device)
-    with torch.cuda.device(lg.device):
-        check(lib().svt_frame_postproc(ptr(lg), n, lg.shape[1], 2, hp.pitch_octave_num + 1,
-                                       2 + hp.pitch_octave_num + 1, hp.pitch_class_num + 1, ptr(octv), ptr(pc),
-                                       current_stream_ptr()))
-    # one device->host transfer for everything the decoder needs (the int32 ids travel as raw bits in an fp32 tensor)
-    packed = torch.cat([lg[:, :2], octv.view(torch.float32).unsqueeze(1), pc.view(torch.float32).unsqueeze(1)], dim=1).cpu()
-    p = torch.sigmoid(packed[:, :2])
-    ids = packed[:, 2:].contiguous().view(torch.int32)
-    return (p[:, 0].contiguous().numpy(), p[:, 1].contiguous().numpy(), ids[:, 0].contiguous().numpy(),
-            ids[:, 1].contiguous().numpy())
+    return _unpack_frames(_pack_frames(logits, hp).cpu())  # ONE device->host transfer
 
 
 def decode_logits(logits: torch.Tensor, hp: "AMTHparams") -> np.ndarray:
@@ -224,21 +211,84 @@ class AMTTranscriber:
         """Evaluation driver replacing the reference's one-utterance-at-a-time loop (speechbrain/core.py:1221-1226,
         train_audio_ssl.py:85-141): utterances of ALL songs are pooled, equal-length ones run in batches of `batch_clips`
         (per-clip normalisation = reference semantics), frames are put back in (song, utterance) order (:88,100) and every
-        song is decoded once."""
+        song is decoded once.
+
+        Nothing on the device path synchronises: every batch's forward, per-frame argmax and device->host copy (into pinned
+        memory, followed by an event) are queued up front; the host then walks the batches in order, waits for a batch's
+        event and runs sigmoid + frame2note for the songs that batch completes -- while the GPU is already running the
+        following batches."""
         hp = self.hp
         songs = [w.to(self.device, torch.float32, non_blocking=True).reshape(-1) for w in wavs]
         jobs = []  # (length, song, utterance index, start, stop)
+        n_utt = []
         for si, w in enumerate(songs):
-            for ui, (a, b) in enumerate(split_song(w.numel(), hp, dur)):
+            spans = split_song(w.numel(), hp, dur)
+            n_utt.append(len(spans))
+            for ui, (a, b) in enumerate(spans):
                 jobs.append((b - a, si, ui, a, b))
         jobs.sort(key=lambda t: (t[0], t[1], t[2]))  # equal lengths become neighbours
-        lgs = self._clip_logits([songs[si][a:b] for _, si, _, a, b in jobs], batch_clips, per_clip_norm)
-        out = {(si, ui): lg for (_, si, ui, _, _), lg in zip(jobs, lgs)}
-        per_song = []
-        for si, w in enumerate(songs):
-            n_utt = len(split_song(w.numel(), hp, dur))
-            per_song.append(torch.cat([out[(si, ui)] for ui in range(n_utt)], dim=0))
-        return decode_logits_many(per_song, hp)
+        stream = torch.cuda.current_stream(self.device)
+        batches = []  # (pinned (frames, 4) tensor, event, [(song, utt, first row, rows)])
+        i = 0
+        while i < len(jobs):
+            j = i
+            while j < len(jobs) and j - i < batch_clips and jobs[j][0] == jobs[i][0]:
+                j += 1
+            lgs = self._clip_logits([songs[si][a:b] for _, si, _, a, b in jobs[i:j]], batch_clips, per_clip_norm)
+            rows, index = 0, []
+            for (_, si, ui, _, _), lg in zip(jobs[i:j], lgs):
+                index.append((si, ui, rows, int(lg.shape[0])))
+                rows += int(lg.shape[0])
+            packed = _pack_frames(torch.cat(lgs, dim=0) if len(lgs) > 1 else lgs[0], hp)
+            host = torch.empty(packed.shape, dtype=torch.float32, pin_memory=True)
+            host.copy_(packed, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            batches.append((host, ev, index))
+            i = j
+        pieces = {}
+        done = [0] * len(songs)
+        results: List[Optional[np.ndarray]] = [None] * len(songs)
+        for host, ev, index in batches:
+            ev.synchronize()
+            p_on, p_off, octv, pc = _unpack_frames(host)
+            for si, ui, r0, n in index:
+                pieces[(si, ui)] = (r0, n, p_on, p_off, octv, pc)
+                done[si] += 1
+                if done[si] == n_utt[si]:
+                    parts = [pieces.pop((si, u)) for u in range(n_utt[si])]
+                    cols = []
+                    for c in range(4):
+                        segs = [arrs[c][r:r + m] for r, m, *arrs in parts]
+                        cols.append(segs[0] if len(segs) == 1 else np.concatenate(segs))
+                    results[si] = decode_arrays(cols[0], cols[1], cols[2], cols[3], hp.onset_threshold, hp.offset_threshold,
+                                                1.0 / hp.frame_rate)
+        for si in range(len(songs)):
+            if results[si] is None:  # a song without a single frame
+                results[si] = np.zeros((0, 3), dtype=np.float64)
+        return results
+
+
+def _pack_frames(logits: torch.Tensor, hp: "AMTHparams") -> torch.Tensor:
+    """(n_frames, 20) CUDA logits -> (n_frames, 4) fp32 on the device: onset / offset logits and the bits of the int32
+    octave / pitch-class argmax (svt_frame_postproc, first max wins) -- everything the decoder needs, in one tensor."""
+    lg = logits.reshape(-1, logits.shape[-1]).contiguous()
+    n = lg.shape[0]
+    octv = torch.empty(n, dtype=torch.int32, device=lg.device)
+    pc = torch.empty(n, dtype=torch.int32, device=lg.device)
+    with torch.cuda.device(lg.device):
+        check(lib().svt_frame_postproc(ptr(lg), n, lg.shape[1], 2, hp.pitch_octave_num + 1,
+                                       2 + hp.pitch_octave_num + 1, hp.pitch_class_num + 1, ptr(octv), ptr(pc),
+                                       current_stream_ptr()))
+    return torch.cat([lg[:, :2], octv.view(torch.float32).unsqueeze(1), pc.view(torch.float32).unsqueeze(1)], dim=1)
+
+
+def _unpack_frames(packed_host: torch.Tensor):
+    """Host half of frame_info: torch's CPU fp32 sigmoid (so frame2note's `==` / `>=` see the reference's bits) + the ids."""
+    p = torch.sigmoid(packed_host[:, :2])
+    ids = packed_host[:, 2:].contiguous().view(torch.int32)
+    return (p[:, 0].contiguous().numpy(), p[:, 1].contiguous().numpy(), ids[:, 0].contiguous().numpy(),
+            ids[:, 1].contiguous().numpy())
 
 
 def decode_logits_many(per_song: Sequence[torch.Tensor], hp: "AMTHparams") -> List[np.ndarray]:

@@ -317,7 +317,10 @@ def run_ours(args):
     # H2D (copy stream) -> forward -> async all-gather -> D2H of the gathered (N*B, T, 20) logits on every rank.
     wav_host = [torch.randn(B, L, generator=torch.Generator().manual_seed(7 + i)).pin_memory() for i in range(2)]
     n_e2e = max(2, args.steps)
-    if world == 1:
+    e2e_s, e2e_api, d2h = float("nan"), "skipped (--no-e2e)", 0
+    if args.no_e2e:
+        pass
+    elif world == 1:
         logits_host = [torch.empty(B, T, 20).pin_memory() for _ in range(2)]
         pipe = eng.pipeline(B, L, depth=2)
 
@@ -380,12 +383,13 @@ def run_ours(args):
         e2e_api = ("pinned host wav -> H2D (copy stream) -> EncoderEngine.forward -> asynchronous NCCL all-gather of the logits -> "
                    "D2H of the gathered (N*B, T, 20) logits to pinned host memory on every rank, double-buffered")
         d2h = world * B * T * 20 * 4
-    e2e_s, _ = max_over_ranks(e2e_s)
+    if not args.no_e2e:
+        e2e_s, _ = max_over_ranks(e2e_s)
     e2e_value = world * B * CLIP_SECONDS / e2e_s
 
     # ---- e2e #2, where the CPU arm ends: wav on the HOST -> notes on the HOST through AMTTranscriber.transcribe_songs (the
     # evaluation driver: H2D, batched per-clip-norm forward, one argmax pass + one D2H, host sigmoid + frame2note per song).
-    songs_host = [wav_host[0][c] for c in range(B)]
+    songs_host = [wav_host[0][c] for c in range(B if not args.no_e2e else 1)]
     for _ in range(2):
         notes = tr.transcribe_songs(songs_host, dur=float(CLIP_SECONDS), batch_clips=B)
     n_notes_runs = max(3, min(args.steps, 7))
@@ -582,6 +586,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the config 4 (audio-visual) and config 5 (long-form) legs")
+    ap.add_argument("--no-e2e", action="store_true", help="development: skip the host-buffer legs (tools/ab_step.py)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the last timed step's logits")
     ap.add_argument("--av-clips", type=int, default=4, help="clips per GPU of the audio-visual leg (config 4: 32 / 8 GPUs)")
     args = ap.parse_args()

@@ -5,7 +5,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvt_b200.so")
+# SVT_B200_LIB points the binding at another build of the same library (A/B measurements of two builds on one box,
+# tools/ab_step.py); the default is the in-tree build next to this file.
+LIB_PATH = os.environ.get("SVT_B200_LIB") or os.path.join(_HERE, "libsvt_b200.so")
 
 MAX_CONV_LAYERS = 8
 

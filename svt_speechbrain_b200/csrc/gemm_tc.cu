@@ -169,6 +169,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_tile = tile / p.n_tiles;
       const int clip = m_tile / p.tiles_per_clip;
       const int tt = m_tile % p.tiles_per_clip;
+      // (column, tap) coordinates of the A view advance incrementally: no integer division in the per-k-block loop, which
+      // shares its sub-partition's issue slots with two epilogue warps (see the producer of gemm_tc2.cu)
+      int kc = 0, tap = 0;
+      const int k_wrap = (p.mode == 0 && p.n_taps > 0) ? p.kb_per_tap * BK : p.k_inner;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * C::kStageBytes;
@@ -177,13 +181,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
           if (p.mode == 0 && p.n_taps > 0) {
             // implicit 2-D conv over flat padded rows: tap = constant row shift, OOB rows read as zero
-            const int tap = kb / p.kb_per_tap;
-            tma_load_3d(sa, &tmA, &full_bar[stage], (kb % p.kb_per_tap) * BK, 0, m_tile * BM + p.tap_off[tap]);
+            tma_load_3d(sa, &tmA, &full_bar[stage], kc, 0, m_tile * BM + p.tap_off[tap]);
             tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_tile * BN);
           } else if (p.mode == 0) {
-            const int k0 = kb * BK;
-            tma_load_3d(sa, &tmA, &full_bar[stage], k0 % p.k_inner, k0 / p.k_inner, m_tile * BM);
-            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n_tile * BN);
+            tma_load_3d(sa, &tmA, &full_bar[stage], kc, tap, m_tile * BM);
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_tile * BN);
           } else if (p.mode == 1) {
             // positional conv: group = n_tile, tap = kb; frames shifted by (tap - pad_left), OOB -> 0
             tma_load_3d(sa, &tmA, &full_bar[stage], n_tile * p.n_stride, tt * BM + kb - p.pad_left, clip);
@@ -196,13 +198,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         __syncwarp();
+        kc += BK;
+        if (kc == k_wrap) { kc = 0; ++tap; }
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-    const uint32_t smem_base = smem_u32(smem);
+    // operand descriptors of stage 0; a stage advances the 16-byte-unit address field by kStageBytes / 16
+    const uint64_t da0 = make_sw128_kmajor_desc(smem_u32(smem));
+    const uint64_t db0 = make_sw128_kmajor_desc(smem_u32(smem) + C::kABytes);
     int stage = 0;
     uint32_t phase = 0;
     int as = 0;
@@ -214,8 +220,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint64_t da = make_sw128_kmajor_desc(smem_base + stage * C::kStageBytes);
-        const uint64_t db = make_sw128_kmajor_desc(smem_base + stage * C::kStageBytes + C::kABytes);
+        const uint64_t da = da0 + static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
+        const uint64_t db = db0 + static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {

@@ -136,23 +136,39 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   setmaxnreg_dec<64>();
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
+    // This loop runs once per k-block on a sub-partition it shares with two epilogue warps, so every instruction in it
+    // competes with the epilogue math for issue slots: a slow producer, not the tensor pipe, was what capped the GELU
+    // GEMM at 66 % pipe activity (profiles/r2_ffn1_producer_stall.txt: the MMA warp waited on `full` 45 % of its time
+    // while this warp was busy 87 % of its time, mostly in the integer division of k0 by k_inner).  Hence: no division
+    // (the (column, tap) coordinates of the A view advance incrementally), addresses formed by adds from per-role constants.
     int stage = 0;
     uint32_t phase = 0;
+    const uint32_t full0_leader = mapa_shared(smem_u32(&full_bar[0]), 0);
+    const uint32_t smem_base = smem_u32(smem);
+    const int b_row_off = static_cast<int>(rank) * (BN2 / 2);
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int n_tile = tile % n_tiles;
       const int m_row = ((tile / n_tiles) * 2 + static_cast<int>(rank)) * BM;
+      const int b_row = n_tile * BN2 + b_row_off;
+      int kc = 0, tap = 0;  // k-block kb covers columns [kc, kc + 64) of tap `tap`: kb * 64 = tap * k_inner + kc
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * kStageBytes2;
-        uint8_t* sb = sa + kABytes;
-        const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
         if (elect_one()) {
+          const uint32_t sa = smem_base + static_cast<uint32_t>(stage * kStageBytes2);
+          const uint32_t bar = full0_leader + static_cast<uint32_t>(stage * 8);
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes2);
-          const int k0 = kb * BK;
-          tma_load_3d_pair(sa, &tmA, leader_full, k0 % k_inner, k0 / k_inner, m_row);
-          tma_load_2d_pair(sb, &tmB, leader_full, k0, n_tile * BN2 + static_cast<int>(rank) * (BN2 / 2));
+          asm volatile(
+              "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+              ::"r"(sa), "l"(&tmA), "r"(bar), "r"(kc), "r"(tap), "r"(m_row)
+              : "memory");
+          asm volatile(
+              "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+              ::"r"(sa + kABytes), "l"(&tmB), "r"(bar), "r"(kb * BK), "r"(b_row)
+              : "memory");
         }
         __syncwarp();
+        kc += BK;
+        if (kc == k_inner) { kc = 0; ++tap; }
         if (++stage == kStages2) { stage = 0; phase ^= 1; }
       }
     }
@@ -160,7 +176,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN2);
-      const uint32_t smem_base = smem_u32(smem);
+      // operand descriptors of stage 0; a stage advances the 16-byte-unit address field by kStageBytes2 / 16
+      const uint64_t da0 = make_sw128_kmajor_desc(smem_u32(smem));
+      const uint64_t db0 = make_sw128_kmajor_desc(smem_u32(smem) + kABytes);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -172,8 +190,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = make_sw128_kmajor_desc(smem_base + stage * kStageBytes2);
-          const uint64_t db = make_sw128_kmajor_desc(smem_base + stage * kStageBytes2 + kABytes);
+          const uint64_t da = da0 + static_cast<uint64_t>(stage * (kStageBytes2 >> 4));
+          const uint64_t db = db0 + static_cast<uint64_t>(stage * (kStageBytes2 >> 4));
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)

@@ -50,7 +50,9 @@ long long svt_debug_launch_count(void);
  * 2 force the tcgen05/TMEM kernel (head_dim 64 only).  "gemm_impl": 0 auto (CTA-pair cta_group::2 kernel when
  * N % 256 == 0 and the problem has enough tiles, else the one-CTA kernel), 1 force the one-CTA kernel, 2 one-CTA kernel with
  * 128-column tiles, 3 force the CTA-pair kernel.  "ln_fold": 1 (default) folds the two per-layer LayerNorms of pre-LN
- * (stable_layer_norm) transformer layers into the neighbouring GEMMs, 0 runs them as separate kernels. */
+ * (stable_layer_norm) transformer layers into the neighbouring GEMMs, 0 runs them as separate kernels.  "rowln_fuse": 1
+ * (default) runs conv -> LayerNorm(512) -> GELU of the layer-norm feature extractors as one kernel per layer
+ * (svt_op_gemm_rowln), 0 as a GEMM followed by a LayerNorm kernel. */
 int svt_set_option(const char* name, int value);
 
 /* development aid: device buffer of 4 x 256 int64 that CTA 0 of the tcgen05 attention kernel fills with clock64()
@@ -218,6 +220,12 @@ int svt_frame2note(const float* p_on, const float* p_off, const int32_t* oct, co
 int svt_op_gemm(const void* a_bf16, long long a_row_stride, int k_inner, const void* w_bf16, const float* bias,
                 const float* resid, float* out_f32, void* out_bf16, int M, int N, int K, int ld_out, int act,
                 void* stream);
+/* conv feature-extractor layer of the layer-norm models (HF modeling_wav2vec2.py:275-299: conv -> LayerNorm(512) -> GELU) in
+ * ONE kernel: out = act(LN(A W^T + bias) * gamma + beta), N = 512, bf16 rows normalised in place while still in L2
+ * (option "rowln_fuse" chooses between this and svt_op_gemm + svt_op_layer_norm inside the encoder). */
+int svt_op_gemm_rowln(const void* a_bf16, long long a_row_stride, int k_inner, const void* w_bf16, const float* bias,
+                      const float* gamma, const float* beta, float eps, int gelu, void* out_bf16, int M, int N, int K,
+                      void* stream);
 /* The two halves of a LayerNorm folded around GEMMs (pre-LN transformer layers, option "ln_fold").  Producer
  * (row_stats_out != NULL, out_f32 != NULL, N % 256 == 0): as svt_op_gemm, and row_stats_out[row][j] = (sum, sum of
  * squares) of columns 128 j .. 128 j + 127 of the fp32 output row.  Consumer (ln_stats != NULL): a holds un-normalised rows x, w = W o gamma,

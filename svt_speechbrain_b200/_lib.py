@@ -84,6 +84,7 @@ _SIGS = {
                               C.c_int, _P]),
     "svt_wavlm_relative_bucket": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "svt_video_transform_u8": (C.c_int, [_P, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P, _P]),
+    "svt_op_gemm_rowln": (C.c_int, [_P, C.c_longlong, C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P]),
     "svt_op_gemm_ln": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "svt_op_row_stats_cast": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "svt_op_posconv": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
@@ -110,6 +111,11 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
+        # SVT_B200_OPTIONS="name=value,..." applies svt_set_option switches at load time (A/B runs of one build)
+        for item in filter(None, os.environ.get("SVT_B200_OPTIONS", "").split(",")):
+            name, _, value = item.partition("=")
+            if L.svt_set_option(name.strip().encode(), int(value)) != 0:
+                raise ValueError(f"SVT_B200_OPTIONS: {L.svt_last_error().decode()}")
         _lib = L
     return _lib
 

@@ -19,7 +19,9 @@ long long launch_count() { return g_launches.load(); }
 static std::atomic<int> g_attention_impl{0};
 static std::atomic<int> g_gemm_impl{0};
 static std::atomic<int> g_ln_fold{1};
+static std::atomic<int> g_rowln_fuse{1};
 int get_option_ln_fold() { return g_ln_fold.load(std::memory_order_relaxed); }
+int get_option_rowln_fuse() { return g_rowln_fuse.load(std::memory_order_relaxed); }
 int get_option_gemm_impl() { return g_gemm_impl.load(std::memory_order_relaxed); }
 int get_option_attention_impl() { return g_attention_impl.load(std::memory_order_relaxed); }
 int num_sms() {
@@ -61,6 +63,11 @@ int svt_set_option(const char* name, int value) {
     g_ln_fold.store(value);
     return kOk;
   }
+  if (n == "rowln_fuse") {
+    if (value < 0 || value > 1) return fail(kInvalidArgument, "rowln_fuse must be 0 (conv GEMM + separate LayerNorm kernel) or 1 (fused)");
+    g_rowln_fuse.store(value);
+    return kOk;
+  }
   return fail(kInvalidArgument, "unknown option " + n);
 }
 void svt_debug_attention_trace(void* dev_buffer_8k) { set_attention_trace_buffer(static_cast<long long*>(dev_buffer_8k)); }
@@ -95,6 +102,24 @@ int svt_op_gemm(const void* a_bf16, long long a_row_stride, int k_inner, const v
   g.M = M; g.N = N; g.K = K; g.k_inner = k_inner;
   g.bias = bias; g.resid = resid; g.out_f32 = out_f32; g.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16);
   g.ld_out = ld_out; g.act = act;
+  return gemm_bf16_tc(g, static_cast<cudaStream_t>(stream));
+}
+
+int svt_op_gemm_rowln(const void* a_bf16, long long a_row_stride, int k_inner, const void* w_bf16, const float* bias,
+                      const float* gamma, const float* beta, float eps, int gelu, void* out_bf16, int M, int N, int K,
+                      void* stream) {
+  if (a_bf16 == nullptr || w_bf16 == nullptr || gamma == nullptr || beta == nullptr || out_bf16 == nullptr)
+    return fail(kInvalidArgument, "null argument");
+  if (k_inner <= 0 || K % k_inner != 0) return fail(kInvalidArgument, "K must be a multiple of k_inner");
+  GemmArgs g;
+  g.a = static_cast<const __nv_bfloat16*>(a_bf16);
+  g.a_dims[0] = k_inner; g.a_dims[1] = K / k_inner; g.a_dims[2] = M;
+  g.a_strides[0] = k_inner; g.a_strides[1] = static_cast<uint64_t>(a_row_stride);
+  g.w = static_cast<const __nv_bfloat16*>(w_bf16); g.w_rows = N; g.w_cols = K;
+  g.M = M; g.N = N; g.K = K; g.k_inner = k_inner;
+  g.bias = bias; g.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); g.ld_out = N; g.act = kActNone;
+  g.rowln_gamma = gamma; g.rowln_beta = beta; g.rowln_eps = eps; g.rowln_gelu = gelu;
+  if (!gemm_rowln_supported(g)) return fail(kUnsupported, "fused row LayerNorm: needs N = 512 and the CTA-pair GEMM (K % 64 == 0)");
   return gemm_bf16_tc(g, static_cast<cudaStream_t>(stream));
 }
 

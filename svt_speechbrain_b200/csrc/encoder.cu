@@ -671,8 +671,15 @@ static int forward_impl(svt_encoder* e, const float* wav, int B, int L, void* ws
     g.M = M; g.N = C; g.K = k * C; g.k_inner = C;
     g.bias = e->conv[i - 1].b; g.out_bf16 = nxt; g.ld_out = C;
     g.act = c.feat_norm_layer ? kActNone : kActGelu;
+    bool fused_ln = false;
+    if (c.feat_norm_layer && get_option_rowln_fuse() != 0) {
+      // conv -> LN(512) -> GELU in one kernel (the rows are normalised in place while still in L2)
+      g.rowln_gamma = e->conv_norm[i - 1].g; g.rowln_beta = e->conv_norm[i - 1].b; g.rowln_eps = 1e-5f; g.rowln_gelu = 1;
+      fused_ln = gemm_rowln_supported(g);
+      if (!fused_ln) g.rowln_gamma = g.rowln_beta = nullptr;
+    }
     SVT_TRY(gemm_bf16_tc(g, s));
-    if (c.feat_norm_layer) {
+    if (c.feat_norm_layer && !fused_ln) {
       LayerNormArgs ln;
       ln.x_bf16 = nxt; ln.y_bf16 = nxt; ln.gamma = e->conv_norm[i - 1].g; ln.beta = e->conv_norm[i - 1].b;
       ln.rows = M; ln.D = C; ln.eps = 1e-5f; ln.gelu = 1;

@@ -28,6 +28,11 @@ struct GemmEpiParams {
   int ln_slots;             // K / 128 (<= kMaxLnSlots)
   const float* ln_colsum;   // consumer: [N] sums of the (gamma-folded) bf16 weight rows; bias holds beta.W + b
   float ln_inv_d, ln_eps;   // 1 / (LN width = K), LN epsilon
+  // row LayerNorm over all N columns fused behind the GEMM (GemmArgs::rowln_*, CTA-pair kernel only)
+  const float* rowln_gamma;
+  const float* rowln_beta;
+  float rowln_eps;
+  int rowln_gelu;
 };
 
 // What the epilogue fetches one tile ahead of its use.
@@ -98,7 +103,7 @@ __device__ __forceinline__ GemmEpiPrefetch gemm_epi_prefetch(const GemmEpiParams
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int row0, int valid, int col0, int n_valid,
                                                    uint32_t tmem_acc, int quad, int half, int lane, uint32_t stage_addr,
-                                                   const GemmEpiPrefetch& pf) {
+                                                   const GemmEpiPrefetch& pf, float2* row_sums = nullptr) {
   constexpr int kColsPerWarp = BN / 2;
   const bool f32_path = (p.out_f32 != nullptr || p.resid != nullptr || p.resid_bf16 != nullptr || p.row_mask != nullptr ||
                          p.act == kActPRelu);
@@ -233,6 +238,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
   } else {
     // bf16-only outputs (QKV, FFN-1 with GELU: issue-bound): the loop is unrolled by two over two register arrays
     // that swap roles, so no accumulator is ever copied between registers
+    float rsum = 0.f, rsq = 0.f;  // row_sums: this thread's row over this warp's columns (after bias, before activation)
     auto chunk = [&](uint32_t (&acc)[32], uint32_t (&nxt)[32], int c) {
       int col, nv;
       chunk_cols(c, &col, &nv);
@@ -258,6 +264,15 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
           v[4 * j + 0] += __uint_as_float(b.x); v[4 * j + 1] += __uint_as_float(b.y);
           v[4 * j + 2] += __uint_as_float(b.z); v[4 * j + 3] += __uint_as_float(b.w);
         }
+      }
+      if (row_sums != nullptr) {
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          s0 += v[j]; s1 += v[j + 1];
+          q0 = fmaf(v[j], v[j], q0); q1 = fmaf(v[j + 1], v[j + 1], q1);
+        }
+        rsum += s0 + s1; rsq += q0 + q1;
       }
       if (p.act == kActGelu) {
 #pragma unroll
@@ -295,6 +310,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
       chunk(ra, rb2, c);
       if (c + 32 < kColsPerWarp) chunk(rb2, ra, c + 32);
     }
+    if (row_sums != nullptr) *row_sums = make_float2(rsum, rsq);
   }
   if constexpr (BN == 256) {
     if (p.row_stats_out != nullptr) {

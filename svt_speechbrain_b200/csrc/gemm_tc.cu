@@ -401,6 +401,7 @@ int gemm_bf16_tc(const GemmArgs& g, cudaStream_t stream) {
     const long long units_pair = static_cast<long long>(ceil_div(g.M, 256)) * (g.N / 256 > 0 ? g.N / 256 : 1);
     want_small = impl == 2 || (impl == 0 && units_pair < kSmallProblemPairUnits);
   }
+  if (g.rowln_gamma != nullptr) return gemm_bf16_tc_pair(g, stream);  // callers check gemm_rowln_supported first
   if (impl == 3 && pair_ok) return gemm_bf16_tc_pair(g, stream);
   if (impl == 0 && pair_ok && !want_small && g.M >= 1024) return gemm_bf16_tc_pair(g, stream);
   KParams kp{};

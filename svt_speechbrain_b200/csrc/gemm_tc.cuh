@@ -56,6 +56,15 @@ struct GemmArgs {
   const float* ln_stats = nullptr;
   const float* ln_colsum = nullptr;
   float ln_eps = 1e-5f;
+  // Row LayerNorm over ALL N output columns (+ optional GELU) fused behind the GEMM (conv feature-extractor layers of the
+  // layer-norm models, HF:275-299: conv -> LN(512) -> GELU): y = act(LN(x.W^T + bias) * gamma + beta), bf16 output only.
+  // Built for N = 512 in the CTA-pair kernel (gemm_rowln_supported): a pair computes both 256-column tiles of a row
+  // block back to back, writes them un-normalised (bf16, they stay in L2) with per-row statistics kept in shared
+  // memory, then normalises the block in place -- the rows never make an extra round trip through HBM.
+  const float* rowln_gamma = nullptr;      // [N]
+  const float* rowln_beta = nullptr;       // [N]
+  float rowln_eps = 1e-5f;
+  int rowln_gelu = 0;
   // ---- shifted-row taps (linear mode only): k-block kb reads A rows (row + tap_off[kb / (k_inner / 64)]), columns
   // (kb % (k_inner / 64)) * 64 .. + 64; K = n_taps * k_inner.  This is a 2-D convolution over feature maps stored as
   // flat rows [frame][y][x] with a zero padding ring: tap (dy, dx) is the constant row offset dy * W_padded + dx.
@@ -65,6 +74,8 @@ struct GemmArgs {
 };
 
 int gemm_bf16_tc(const GemmArgs& g, cudaStream_t stream);
+// true when g (with rowln_gamma set) can run with the LayerNorm fused; otherwise run the GEMM plain + layer_norm()
+bool gemm_rowln_supported(const GemmArgs& g);
 
 // bf16 tiled tensor map with 128-byte swizzle; strides in elements for dims 1..rank-1
 int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,

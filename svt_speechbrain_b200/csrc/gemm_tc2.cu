@@ -89,9 +89,86 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
 }
 
+// Fused row LayerNorm (GemmArgs::rowln_*), N = 2 * BN2 = 512 columns.  Every epilogue warp parks the (sum, sum of squares) of
+// its 32 rows x 128 columns in the unused last kilobyte of its staging tile: [unit parity][n tile][lane] float2.
+constexpr int kRowLnSlot = 3072;
+constexpr int kRowLnN = 2 * BN2;
+
+// Second half of the fused LayerNorm: this CTA's 128 rows x 512 columns were just written un-normalised (bf16) by its own
+// epilogue warps and are still in L2; epilogue warp ew normalises rows [16 ew, 16 ew + 16) in place, a lane owning columns
+// [8 lane, +8) and [256 + 8 lane, +8) (whole 512-byte halves of a row per warp instruction).
+__device__ __forceinline__ void rowln_finish(const GemmEpiParams& p, int row0, int valid, const uint8_t* stage_area, int upar,
+                                             int ew, int lane) {
+  float g[16], b[16];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(p.rowln_gamma + h * BN2 + 8 * lane + 4 * v));
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(p.rowln_beta + h * BN2 + 8 * lane + 4 * v));
+      g[8 * h + 4 * v + 0] = gv.x; g[8 * h + 4 * v + 1] = gv.y; g[8 * h + 4 * v + 2] = gv.z; g[8 * h + 4 * v + 3] = gv.w;
+      b[8 * h + 4 * v + 0] = bv.x; b[8 * h + 4 * v + 1] = bv.y; b[8 * h + 4 * v + 2] = bv.z; b[8 * h + 4 * v + 3] = bv.w;
+    }
+  // The rows come back from L2 (~700 cycles) and two epilogue warps per sub-partition cannot hide that with math, so they
+  // are fetched asynchronously (cp.async.cg, L2 only: coherent with the other warps' stores ordered by the barrier) three
+  // rows ahead into the first 3 KB of this warp's staging tile; a lane copies and later reads only its own 2 x 16 bytes.
+  constexpr int kAhead = 3;
+  const int r_begin = 16 * ew;
+  const int r_end = min(r_begin + 16, valid);
+  auto row_ptr = [&](int r) { return p.out_bf16 + static_cast<size_t>(row0 + r) * static_cast<size_t>(p.ld_out); };
+  const uint32_t slot0 = smem_u32(stage_area + ew * kEpiStageBytes) + 16 * lane;
+  auto fetch = [&](int r) {
+    if (r < r_end) {
+      const uint32_t dst = slot0 + static_cast<uint32_t>(((r - r_begin) % kAhead) * 1024);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(row_ptr(r) + 8 * lane) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512), "l"(row_ptr(r) + BN2 + 8 * lane) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // one group per row, empty past the end: the wait below counts groups
+  };
+#pragma unroll
+  for (int i = 0; i < kAhead; ++i) fetch(r_begin + i);
+#pragma unroll 1
+  for (int r = r_begin; r < r_end; ++r) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kAhead - 1) : "memory");
+    const uint32_t src = slot0 + static_cast<uint32_t>(((r - r_begin) % kAhead) * 1024);
+    const uint4 x0 = epi_lds128(src), x1 = epi_lds128(src + 512);
+    // four partial statistics of the row: column halves (warps q, q + 4) of the two tiles, fixed order
+    const uint8_t* st = stage_area + (r >> 5) * kEpiStageBytes + kRowLnSlot + upar * 512 + (r & 31) * 8;
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const float2 v = *reinterpret_cast<const float2*>(st + hh * 4 * kEpiStageBytes + t * 256);
+        sum += v.x; sq += v.y;
+      }
+    const float mean = sum * (1.0f / kRowLnN);
+    const float rstd = rsqrtf(fmaxf(sq * (1.0f / kRowLnN) - mean * mean, 0.f) + p.rowln_eps);
+    const float shift = -mean * rstd;
+    const uint32_t w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    float y[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
+      y[2 * j] = fmaf(fmaf(lo, rstd, shift), g[2 * j], b[2 * j]);
+      y[2 * j + 1] = fmaf(fmaf(hi, rstd, shift), g[2 * j + 1], b[2 * j + 1]);
+    }
+    fetch(r + kAhead);  // this row's slot is free again: its 32 bytes are in registers
+    if (p.rowln_gelu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) y[j] = gelu_erf(y[j]);
+    }
+    *reinterpret_cast<uint4*>(row_ptr(r) + 8 * lane) =
+        make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+    *reinterpret_cast<uint4*>(row_ptr(r) + BN2 + 8 * lane) =
+        make_uint4(pack_bf16x2(y[8], y[9]), pack_bf16x2(y[10], y[11]), pack_bf16x2(y[12], y[13]), pack_bf16x2(y[14], y[15]));
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmEpiParams p,
-                int k_inner, int num_kb, int m_pairs, int n_tiles) {
+                int k_inner, int num_kb, int m_pairs, int n_tiles, int n_inner) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_area = smem + kStages2 * kStageBytes2;  // 8 epilogue warps x 4 KB transpose tiles
@@ -109,7 +186,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
-  const int num_tiles = m_pairs * n_tiles;
+  // Work unit = n_inner consecutive tiles (tile = m_pair * n_tiles + n_tile, n fastest) handled back to back by one pair:
+  // n_inner = 1 normally; n_inner = n_tiles with the fused row LayerNorm, so that a pair owns whole output rows.
+  const int num_units = m_pairs * n_tiles / n_inner;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -146,7 +225,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t full0_leader = mapa_shared(smem_u32(&full_bar[0]), 0);
     const uint32_t smem_base = smem_u32(smem);
     const int b_row_off = static_cast<int>(rank) * (BN2 / 2);
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+    for (int unit = pair; unit < num_units; unit += num_pairs)
+    for (int ui = 0; ui < n_inner; ++ui) {
+      const int tile = unit * n_inner + ui;
       const int n_tile = tile % n_tiles;
       const int m_row = ((tile / n_tiles) * 2 + static_cast<int>(rank)) * BM;
       const int b_row = n_tile * BN2 + b_row_off;
@@ -183,7 +264,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      for (int unit = pair; unit < num_units; unit += num_pairs)
+      for (int ui = 0; ui < n_inner; ++ui) {
         mbar_wait(&tempty_bar[as], aphase ^ 1);  // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN2);
@@ -213,36 +295,59 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quad = warp & 3;
     const int half = (warp - kEpiWarp0) >> 2;
     const uint32_t stage_mine = smem_u32(stage_area + (warp - kEpiWarp0) * kEpiStageBytes);
+    const bool rowln = p.rowln_gamma != nullptr;
+    auto tile_of = [&](int unit, int ui, int* row0, int* col0) {
+      const int tile = unit * n_inner + ui;
+      *row0 = ((tile / n_tiles) * 2 + static_cast<int>(rank)) * BM;
+      *col0 = (tile % n_tiles) * BN2;
+    };
     GemmEpiPrefetch pf_next{};
-    if (pair < num_tiles) {
-      const int r0 = ((pair / n_tiles) * 2 + static_cast<int>(rank)) * BM;
-      pf_next = gemm_epi_prefetch<BN2>(p, r0, p.M - r0, (pair % n_tiles) * BN2, BN2, quad, half, lane);
+    if (pair < num_units) {
+      int r0, c0;
+      tile_of(pair, 0, &r0, &c0);
+      pf_next = gemm_epi_prefetch<BN2>(p, r0, p.M - r0, c0, BN2, quad, half, lane);
     }
     const uint32_t leader_tempty0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int n_tile = tile % n_tiles;
-      const int row0 = ((tile / n_tiles) * 2 + static_cast<int>(rank)) * BM;
-      const int valid = p.M - row0;
-      const GemmEpiPrefetch pf_cur = pf_next;
-      {
-        const int nt = tile + num_pairs;
-        if (nt < num_tiles) {
-          const int nrow0 = ((nt / n_tiles) * 2 + static_cast<int>(rank)) * BM;
-          pf_next = gemm_epi_prefetch<BN2>(p, nrow0, p.M - nrow0, (nt % n_tiles) * BN2, BN2, quad, half, lane);
-          if (p.resid != nullptr) gemm_prefetch_resid<BN2>(p, nrow0, p.M - nrow0, (nt % n_tiles) * BN2, BN2);
+    int upar = 0;  // parity of the unit: double-buffers the row statistics of the fused LayerNorm
+    for (int unit = pair; unit < num_units; unit += num_pairs) {
+      for (int ui = 0; ui < n_inner; ++ui) {
+        int row0, col0;
+        tile_of(unit, ui, &row0, &col0);
+        const int valid = p.M - row0;
+        const GemmEpiPrefetch pf_cur = pf_next;
+        {
+          int nu = unit, ni = ui + 1;
+          if (ni == n_inner) { ni = 0; nu += num_pairs; }
+          if (nu < num_units) {
+            int nrow0, ncol0;
+            tile_of(nu, ni, &nrow0, &ncol0);
+            pf_next = gemm_epi_prefetch<BN2>(p, nrow0, p.M - nrow0, ncol0, BN2, quad, half, lane);
+            if (p.resid != nullptr) gemm_prefetch_resid<BN2>(p, nrow0, p.M - nrow0, ncol0, BN2);
+          }
         }
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        float2 rs = make_float2(0.f, 0.f);
+        gemm_epilogue_tile<BN2>(p, row0, valid, col0, BN2, tmem_base + static_cast<uint32_t>(as * BN2), quad, half, lane,
+                                stage_mine, pf_cur, rowln ? &rs : nullptr);
+        // all of this warp's TMEM reads are complete -> release the accumulator stage to the leader's MMA thread
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_tempty0 + static_cast<uint32_t>(as * 8));
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        if (rowln)  // (sum, sum of squares) of row quad * 32 + lane over this warp's 128 columns of tile ui
+          *reinterpret_cast<float2*>(stage_area + (warp - kEpiWarp0) * kEpiStageBytes + kRowLnSlot + (upar * 2 + ui) * 256 + lane * 8) = rs;
       }
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-      gemm_epilogue_tile<BN2>(p, row0, valid, n_tile * BN2, BN2, tmem_base + static_cast<uint32_t>(as * BN2), quad, half, lane,
-                              stage_mine, pf_cur);
-      // all of this warp's TMEM reads are complete -> release the accumulator stage to the leader's MMA thread
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(leader_tempty0 + static_cast<uint32_t>(as * 8));
-      if (++as == 2) { as = 0; aphase ^= 1; }
+      if (rowln) {
+        // every epilogue warp has stored its un-normalised part of these 128 rows and published its statistics
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        int row0, col0;
+        tile_of(unit, 0, &row0, &col0);
+        rowln_finish(p, row0, p.M - row0, stage_area, upar, warp - kEpiWarp0, lane);
+        upar ^= 1;
+      }
     }
   }
 
@@ -257,6 +362,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 }  // namespace
 
+bool gemm_rowln_supported(const GemmArgs& g) {
+  return gemm_pair_supported(g) && g.N == kRowLnN && g.ld_out == kRowLnN && g.out_bf16 != nullptr && g.out_f32 == nullptr &&
+         g.resid == nullptr && g.resid_bf16 == nullptr && g.row_mask == nullptr && g.act == kActNone && g.n_taps == 0 &&
+         g.ln_stats == nullptr && g.row_stats_out == nullptr && g.rowln_beta != nullptr && get_option_gemm_impl() != 1;
+}
+
 bool gemm_pair_supported(const GemmArgs& g) {
   return g.mode == 0 && g.N % BN2 == 0 && g.K % BK == 0 && (g.k_inner > 0 ? g.k_inner : g.K) % BK == 0 && num_sms() % 2 == 0;
 }
@@ -269,6 +380,12 @@ int gemm_bf16_tc_pair(const GemmArgs& g, cudaStream_t stream) {
   p.ld_out = g.ld_out; p.act = g.act; p.alpha = g.alpha; p.resid_bf16 = g.resid_bf16; p.row_mask = g.row_mask;
   p.row_stats_out = g.row_stats_out; p.ln_stats = g.ln_stats; p.ln_colsum = g.ln_colsum;
   p.ln_slots = g.K / 128; p.ln_inv_d = 1.0f / static_cast<float>(g.K); p.ln_eps = g.ln_eps;
+  int n_inner = 1;
+  if (g.rowln_gamma != nullptr) {
+    if (!gemm_rowln_supported(g)) return fail(kUnsupported, "gemm: fused row LayerNorm needs N = 512 bf16 rows in the CTA-pair kernel");
+    p.rowln_gamma = g.rowln_gamma; p.rowln_beta = g.rowln_beta; p.rowln_eps = g.rowln_eps; p.rowln_gelu = g.rowln_gelu;
+    n_inner = g.N / BN2;
+  }
   const int k_inner = g.k_inner > 0 ? g.k_inner : g.K;
   CUtensorMap tmA, tmB;
   const uint32_t abox[3] = {BK, 1, BM};
@@ -281,10 +398,10 @@ int gemm_bf16_tc_pair(const GemmArgs& g, cudaStream_t stream) {
   if (first_use_on_device(attr_seen)) SVT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
   const int m_pairs = ceil_div(g.M, 2 * BM);
   const int n_tiles = g.N / BN2;
-  const int tiles = m_pairs * n_tiles;
+  const int units = m_pairs * n_tiles / n_inner;
   const int max_pairs = num_sms() / 2;
-  const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
-  gemm_tc2_kernel<<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles);
+  const int grid = 2 * (units < max_pairs ? units : max_pairs);
+  gemm_tc2_kernel<<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles, n_inner);
   SVT_POST_LAUNCH();
   return kOk;
 }

@@ -423,3 +423,34 @@ def test_wavlm_bias_table_cache_is_bounded():
         out = tr.logits(torch.randn(1, 4000 + 320 * (i + 1), generator=g).cuda())
         assert torch.isfinite(out).all()
     assert torch.equal(tr.logits(first), ref)
+
+
+def test_fused_feature_extractor_layer_norm_matches_separate_kernels():
+    """Option "rowln_fuse": conv -> LayerNorm(512) -> GELU of the layer-norm feature extractor as one kernel per layer
+    (default) vs GEMM + LayerNorm kernel: same logits within bf16 noise, both within tolerance of the oracle."""
+    from oracle import make_golden as mg
+    from oracle import wav2vec2_oracle as wo
+    import svt_speechbrain_b200 as svt
+    from svt_speechbrain_b200._lib import check, lib
+
+    cfg = wo.W2V2Config.large()
+    lobe, lin, sd, head = _build(cfg)
+    tr = svt.AMTTranscriber(lobe, lin)
+    wav = mg.synth_wav(3, 40123, seed=12)
+    with torch.no_grad():
+        ref = wo.amt_logits(cfg, sd, head, wav).numpy()
+    tr.logits(wav.cuda())  # engine built, weights packed: the launch counts below are forward passes only
+    n0 = lib().svt_debug_launch_count()
+    try:
+        check(lib().svt_set_option(b"rowln_fuse", 0))
+        sep = tr.logits(wav.cuda()).cpu()
+        n1 = lib().svt_debug_launch_count()
+        check(lib().svt_set_option(b"rowln_fuse", 1))
+        fused = tr.logits(wav.cuda()).cpu()
+        n2 = lib().svt_debug_launch_count()
+    finally:
+        lib().svt_set_option(b"rowln_fuse", 1)
+    _check_logits(sep, ref, "separate conv LayerNorm kernels")
+    _check_logits(fused, ref, "fused conv LayerNorm")
+    assert (n1 - n0) - (n2 - n1) == 6          # the six layer_norm launches of conv layers 1-6 are gone
+    assert float((sep - fused).abs().max()) < 5e-2

@@ -87,3 +87,48 @@ def test_pair_gemm_conv_view(k, stride):
     err = (of - ref).abs().max().item()
     print(f"pair conv view k={k} s={stride}: max abs err {err:.3e}")
     assert err < 2e-3
+
+
+@pytest.mark.parametrize("M,K,conv", [(256, 1024, False), (1000, 1536, True), (128 * 2 * 74 * 3 + 77, 1024, True), (40000, 512, False)])
+def test_gemm_with_fused_row_layer_norm_gelu(M, K, conv):
+    """svt_op_gemm_rowln: conv-as-GEMM -> LayerNorm(512) -> GELU in one kernel (HF:275-299) vs fp32 torch.  Covers a single
+    unit, a ragged tail, more than two units per CTA pair (the statistics slots are double-buffered by unit parity) and the
+    overlapping-row conv view (k = 2 or 3, stride 2)."""
+    import torch.nn.functional as F
+    from svt_speechbrain_b200._lib import check, current_stream_ptr, lib, ptr
+
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    N = 512
+    if conv:  # rows of C_in = 512 channels, output row m reads input rows 2m .. 2m + taps - 1 (contiguous taps * C_in elements)
+        cin, taps = 512, K // 512
+        x = (torch.randn(2 * M + taps, cin, device="cuda", generator=g) * 0.7).bfloat16()
+        a_buf, stride, k_inner = x, 2 * cin, cin
+        rows = torch.arange(M) if M <= 4096 else torch.cat([torch.arange(0, 300), torch.arange(M // 2, M // 2 + 300),
+                                                            torch.arange(M - 200, M)])
+        a_ref = torch.stack([x[2 * int(m): 2 * int(m) + taps].reshape(-1) for m in rows]).float()
+    else:
+        a_buf = (torch.randn(M, K, device="cuda", generator=g) * 0.7).bfloat16()
+        a_ref, stride, k_inner, rows = a_buf.float(), K, K, torch.arange(M)
+    rows = rows.cuda()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5 * 2.0).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g) * 0.3
+    gamma = 1.0 + 0.2 * torch.randn(N, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    check(lib().svt_op_gemm_rowln(ptr(a_buf), stride, k_inner, ptr(w), ptr(bias), ptr(gamma), ptr(beta), 1e-5, 1, ptr(out), M, N, K,
+                                  current_stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    pre = a_ref @ w.float().t() + bias
+    ref = F.gelu(F.layer_norm(pre, (N,), gamma, beta, 1e-5))
+    got = out[rows].float()
+    err = float((got - ref).abs().max())
+    rel = float((got - ref).norm() / ref.norm())
+    print(f"fused conv+LN+GELU M={M} K={K} conv={conv}: max-abs {err:.3e} rel-L2 {rel:.3e}")
+    assert rel < 6e-3 and err < 6e-2
+    # and the two-kernel route gives the same rows up to the rounding of the statistics
+    two = torch.empty_like(out)
+    check(lib().svt_op_gemm(ptr(a_buf), stride, k_inner, ptr(w), ptr(bias), None, None, ptr(two), M, N, K, N, 0, current_stream_ptr()))
+    check(lib().svt_op_layer_norm(None, ptr(two), ptr(gamma), ptr(beta), ptr(two), None, M, N, 1e-5, 1, current_stream_ptr()))
+    torch.cuda.synchronize()
+    assert float((two.float() - out.float()).abs().max()) < 4e-2

@@ -113,6 +113,23 @@ def main():
         gemm("conv1 k3s2 (implicit)", 1024000, 512, 1536, k_inner=512, row_stride=1024, out=out)
         gemm("conv2 k3s2 (implicit)", 512000, 512, 1536, k_inner=512, row_stride=1024, out=out)
         gemm("conv5 k2s2 (implicit)", 64000, 512, 1024, k_inner=512, row_stride=1024, out=out)
+    if "conv" in which:
+        for nm, Mc, Kc in (("conv1", 1024000, 1536), ("conv2", 512000, 1536), ("conv5", 64000, 1024)):
+            a = torch.randn(2 * Mc + 8, 512, device=dev).bfloat16()
+            w = (torch.randn(512, Kc, device=dev) / Kc ** 0.5).bfloat16()
+            bias, gam, bet = torch.zeros(512, device=dev), torch.ones(512, device=dev), torch.zeros(512, device=dev)
+            o = torch.empty(Mc, 512, device=dev, dtype=torch.bfloat16)
+            s_ = current_stream_ptr()
+            fn = lambda: check(lib().svt_op_gemm_rowln(ptr(a), 1024, 512, ptr(w), ptr(bias), ptr(gam), ptr(bet), 1e-5, 1, ptr(o), Mc, 512, Kc, s_))
+            us = timeit(fn)
+
+            def two():
+                check(lib().svt_op_gemm(ptr(a), 1024, 512, ptr(w), ptr(bias), None, None, ptr(o), Mc, 512, Kc, 512, 0, s_))
+                check(lib().svt_op_layer_norm(None, ptr(o), ptr(gam), ptr(bet), ptr(o), None, Mc, 512, 1e-5, 1, s_))
+            us2 = timeit(two)
+            print(f"{nm + ' + LN(512) + GELU fused':34s} M={Mc:8d} N=  512 K={Kc:5d}  {us:9.1f} us  {2.0 * Mc * 512 * Kc / us / 1e6:7.1f} TFLOP/s   "
+                  f"(GEMM + LayerNorm kernel: {us2:.1f} us)", flush=True)
+            out[nm + " fused ln"] = {"us": us, "us_two_kernels": us2}
     if "posconv" in which or "conv" in which:
         D, G, taps = 1024, 16, 128
         x = torch.randn(B * Ta, D, device=dev).bfloat16()

@@ -20,6 +20,8 @@ static std::atomic<int> g_attention_impl{0};
 static std::atomic<int> g_gemm_impl{0};
 static std::atomic<int> g_ln_fold{1};
 static std::atomic<int> g_rowln_fuse{1};
+static std::atomic<int> g_conv0_impl{0};
+int get_option_conv0_impl() { return g_conv0_impl.load(std::memory_order_relaxed); }
 int get_option_ln_fold() { return g_ln_fold.load(std::memory_order_relaxed); }
 int get_option_rowln_fuse() { return g_rowln_fuse.load(std::memory_order_relaxed); }
 int get_option_gemm_impl() { return g_gemm_impl.load(std::memory_order_relaxed); }
@@ -61,6 +63,11 @@ int svt_set_option(const char* name, int value) {
   if (n == "ln_fold") {
     if (value < 0 || value > 1) return fail(kInvalidArgument, "ln_fold must be 0 (separate LayerNorm kernels) or 1 (folded)");
     g_ln_fold.store(value);
+    return kOk;
+  }
+  if (n == "conv0_impl") {
+    if (value < 0 || value > 1) return fail(kInvalidArgument, "conv0_impl must be 0 (auto: tensor-core kernel for layer-norm models) or 1 (SIMT kernel)");
+    g_conv0_impl.store(value);
     return kOk;
   }
   if (n == "rowln_fuse") {
@@ -209,7 +216,19 @@ int svt_op_conv0(const float* wav, int B, int L, const float* w_kc, const float*
   a.wav = wav; a.B = B; a.L = L; a.T = (L - 10) / 5 + 1; a.t_alloc = t_alloc;
   a.w = w_kc; a.bias = bias; a.gamma = gamma; a.beta = beta; a.in_stats = normalize ? stats_scratch : nullptr;
   a.out = static_cast<__nv_bfloat16*>(out_bf16); a.layer_mode = 1;
-  return conv0_forward(a, s);
+  void* tables = nullptr;
+  if (get_option_conv0_impl() != 1) {  // test hook: tables built per call (the encoder builds them once at finalize)
+    SVT_CUDA(cudaMalloc(&tables, conv0_tables_bytes()));
+    const int rc = conv0_build_tables(w_kc, bias, tables, s);
+    if (rc != kOk) { cudaFree(tables); return rc; }
+    a.tc_tables = tables;
+  }
+  const int rc = conv0_forward(a, s);
+  if (tables != nullptr) {
+    cudaStreamSynchronize(s);
+    cudaFree(tables);
+  }
+  return rc;
 }
 
 }  // extern "C"

@@ -179,6 +179,11 @@ int svt::encoder_finalize(svt_encoder* e) {
   if (c.conv_bias) SVT_TRY(pack_vec(pool, reg, fe + "0.conv.bias", C, 1.f, &e->conv0_b));
   else SVT_TRY(zero_vec(pool, C, 0.f, &e->conv0_b));
   SVT_TRY(pack_norm(pool, reg, fe + "0.layer_norm.", C, &e->conv0_norm));  // LN (large) or GroupNorm (base)
+  e->conv0_tab = nullptr;
+  if (c.feat_norm_layer && C == 512 && c.conv_kernel[0] == 10 && c.conv_stride[0] == 5) {
+    SVT_TRY(pool.alloc(conv0_tables_bytes(), &e->conv0_tab));
+    SVT_TRY(conv0_build_tables(e->conv0_w, e->conv0_b, e->conv0_tab, 0));
+  }
 
   // conv layers 1..: (C, C, k) -> [C][k][C_in] bf16 so that K index = tap * C_in + ci
   for (int i = 1; i < c.num_conv_layers; ++i) {
@@ -650,7 +655,7 @@ static int forward_impl(svt_encoder* e, const float* wav, int B, int L, void* ws
   c0.w = e->conv0_w; c0.bias = e->conv0_b; c0.gamma = e->conv0_norm.g; c0.beta = e->conv0_norm.b;
   c0.in_stats = c.normalize_wav ? stats_in : nullptr;
   c0.stats_stride = stats_stride;
-  c0.out = bufA; c0.layer_mode = c.feat_norm_layer; c0.chan_stats = chan;
+  c0.out = bufA; c0.layer_mode = c.feat_norm_layer; c0.chan_stats = chan; c0.tc_tables = e->conv0_tab;
   SVT_TRY(conv0_forward(c0, s));
   if (!c.feat_norm_layer)
     SVT_TRY(groupnorm_gelu_apply(bufA, chan, e->conv0_norm.g, e->conv0_norm.b, B, c0.T, p.T0a, C, s));

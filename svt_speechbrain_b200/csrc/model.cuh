@@ -102,6 +102,7 @@ struct svt_encoder {
   // packed weights
   float* conv0_w = nullptr;  // [k][C] fp32
   float* conv0_b = nullptr;
+  void* conv0_tab = nullptr;  // tables of the tensor-core conv0 kernel (layer-norm feature extractors)
   svt::NormW conv0_norm;
   std::vector<svt::LinearW> conv;   // layers 1..n-1: [C, k*C_in]
   std::vector<svt::NormW> conv_norm;

@@ -87,8 +87,14 @@ struct Conv0Args {
   __nv_bfloat16* out = nullptr;
   int layer_mode = 1;
   double* chan_stats = nullptr;  // group mode: [B][C][2] sums (zeroed by the launcher)
+  // layer mode: tables of the tensor-core kernel (conv0_build_tables; conv0_tables_bytes() bytes, 16-byte aligned).
+  // null (or option "conv0_impl" = 1) runs the SIMT kernel.
+  const void* tc_tables = nullptr;
 };
 int conv0_forward(const Conv0Args& a, cudaStream_t stream);
+size_t conv0_tables_bytes();
+int conv0_build_tables(const float* w_kc, const float* bias, void* tables, cudaStream_t stream);
+int get_option_conv0_impl();  // "conv0_impl": 0 auto (tensor-core kernel for layer-norm models), 1 SIMT kernel
 
 // group-norm apply (+GELU) for the base model's layer 0: in-place on (B, t_alloc, C) bf16
 int groupnorm_gelu_apply(__nv_bfloat16* x, const double* chan_stats, const float* gamma, const float* beta, int B, int T,

@@ -253,6 +253,203 @@ conv0_kernel(const float* __restrict__ wav, int L, int T, int t_alloc, const flo
   }
 }
 
+// ------------------------------------------------------------------------------------ conv layer 0 on the tensor cores
+// Layer-norm models (wav2vec2-large ...): (x - mean) * rstd -> conv(k = 10, s = 5) + bias -> LN(512) -> GELU -> bf16.
+// The SIMT kernel above spends 10 FFMA + shuffles per output on the dot products and two warp reductions per frame on the
+// LayerNorm statistics; it is bound by instruction issue (76 % of the issue slots, 0.23 of the HBM roof).  Here
+//   * the statistics of a frame come from closed forms of its 10 input samples:  sum_c y_c = W1 . x + B1  and
+//     sum_c y_c^2 = x^T G x + 2 H . x + B2  with G = W^T W (10 x 10), H = W^T b -- ~80 FFMA per FRAME, one lane per frame;
+//   * the dot products run as mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with fp32 precision kept by splitting both
+//     operands into bf16 hi + lo parts (x_hi w_hi + x_lo w_hi + x_hi w_lo: relative error ~2^-17);
+//   * the K = 16 operand has six spare slots: slot 10 carries rstd_f (A) x bias_c (B) and slot 11 carries -mean_f rstd_f
+//     (A) x 1 (B), and the taps of A are pre-scaled by rstd_f, so the accumulator IS the normalised value
+//     z = (conv + bias - mean_f) * rstd_f and the epilogue is one FFMA (gamma, beta) + GELU per element;
+//   * the columns of the B operand are permuted so that four consecutive n-tiles leave 8 CONTIGUOUS channels in a thread:
+//     one 16-byte store per row and thread, a quad covers 64 bytes.
+// A warp handles 32 frames (two m16 tiles) at a time so every B fragment / (gamma, beta) vector read from shared memory
+// feeds two MMAs rows.  Tables (conv0_build_tables): B fragments [64 n-tiles][32 lanes] uint4 {hi k0-1, hi k8-9, lo k0-1,
+// lo k8-9} + the 77 closed-form coefficients.
+constexpr int kC0Tiles = kC0 / 8;                      // 64 n-tiles
+constexpr int kC0FragBytes = kC0Tiles * 32 * 16;       // 32 KB
+constexpr int kC0QuadFloats = 80;                      // G' 55 (upper triangle, off-diagonals doubled), 2H 10, W1 10, B1, B2
+constexpr int kC0FramesPerWarp = 32;
+
+__device__ __forceinline__ int conv0_tile_channel(int tile, int col) {  // column `col` (0..7) of n-tile `tile` -> channel
+  return 32 * (tile >> 2) + 8 * (col >> 1) + 2 * (tile & 3) + (col & 1);
+}
+__device__ __forceinline__ void split_bf16(float v, float& hi, float& lo) {
+  hi = __bfloat162float(__float2bfloat16_rn(v));
+  lo = v - hi;
+}
+
+__global__ void __launch_bounds__(256) conv0_tables_kernel(const float* __restrict__ w /*[k][C]*/, const float* __restrict__ bias,
+                                                           uint4* __restrict__ frag, float* __restrict__ quad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kC0Tiles * 32) {
+    const int tile = i >> 5, lane = i & 31, g = lane >> 2, tig = lane & 3;
+    const int c = conv0_tile_channel(tile, g);
+    auto val = [&](int k) -> float {
+      if (k < kK0) return w[k * kC0 + c];
+      if (k == 10) return bias != nullptr ? bias[c] : 0.f;
+      return k == 11 ? 1.f : 0.f;
+    };
+    float hi[4], lo[4];
+    const int ks[4] = {2 * tig, 2 * tig + 1, 2 * tig + 8, 2 * tig + 9};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      split_bf16(val(ks[j]), hi[j], lo[j]);
+      if (ks[j] == 11) lo[j] = 0.f;
+    }
+    frag[i] = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 77) {
+    // closed-form coefficients in double: entry e < 55 is G'(j, k), j <= k
+    const int e = threadIdx.x;
+    double acc = 0.0;
+    if (e < 55) {
+      int j = 0, rem = e;
+      while (rem >= kK0 - j) { rem -= kK0 - j; ++j; }
+      const int k = j + rem;
+      for (int c = 0; c < kC0; ++c) acc += static_cast<double>(w[j * kC0 + c]) * w[k * kC0 + c];
+      if (k != j) acc *= 2.0;
+    } else if (e < 65) {
+      for (int c = 0; c < kC0; ++c) acc += 2.0 * w[(e - 55) * kC0 + c] * (bias != nullptr ? bias[c] : 0.f);
+    } else if (e < 75) {
+      for (int c = 0; c < kC0; ++c) acc += w[(e - 65) * kC0 + c];
+    } else if (e == 75) {
+      for (int c = 0; c < kC0; ++c) acc += bias != nullptr ? bias[c] : 0.f;
+    } else {
+      for (int c = 0; c < kC0; ++c) acc += bias != nullptr ? static_cast<double>(bias[c]) * bias[c] : 0.0;
+    }
+    quad[e] = static_cast<float>(acc);
+  }
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// first MMA of an accumulator: C = 0 comes from the zero register instead of 4 MOVs per fragment
+__device__ __forceinline__ void mma_bf16_16816_zero(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %10, %10, %10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+
+__global__ void __launch_bounds__(256, 2)
+conv0_tc_kernel(const float* __restrict__ wav, int L, int T, int t_alloc, const uint4* __restrict__ frag,
+                const float* __restrict__ quad, const float* __restrict__ gamma, const float* __restrict__ beta,
+                const double* __restrict__ in_stats, double n_in, __nv_bfloat16* __restrict__ out, int stats_stride, int iters) {
+  __shared__ __align__(16) uint4 sfrag[kC0Tiles * 32];
+  __shared__ __align__(16) float sgamma[kC0];
+  __shared__ __align__(16) float sbeta[kC0];
+  __shared__ float squad[kC0QuadFloats];
+  for (int i = threadIdx.x; i < kC0Tiles * 32; i += blockDim.x) sfrag[i] = frag[i];
+  for (int i = threadIdx.x; i < kC0; i += blockDim.x) { sgamma[i] = gamma[i]; sbeta[i] = beta[i]; }
+  if (threadIdx.x < 77) squad[threadIdx.x] = quad[threadIdx.x];
+  __syncthreads();
+  float mean = 0.f, rstd = 1.f;
+  if (in_stats != nullptr) mean_rstd_from_stats(in_stats + static_cast<size_t>(blockIdx.y) * stats_stride, n_in, 1e-5f, mean, rstd);
+  const float in_shift = -mean * rstd;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+  const float* x = wav + static_cast<size_t>(blockIdx.y) * L;
+  __nv_bfloat16* o = out + static_cast<size_t>(blockIdx.y) * t_alloc * kC0;
+
+  for (int it = 0; it < iters; ++it) {
+    const int f0 = ((blockIdx.x * iters + it) * 8 + warp) * kC0FramesPerWarp;
+    if (f0 >= t_alloc) break;
+    // ---- LayerNorm statistics of frame f0 + lane from its 10 normalised samples (closed forms)
+    float mu = 0.f, rs = 0.f;
+    {
+      const int f = f0 + lane;
+      float xv[kK0];
+#pragma unroll
+      for (int j = 0; j < kK0; ++j) xv[j] = (f < T) ? fmaf(__ldg(x + kS0 * f + j), rstd, in_shift) : 0.f;
+      float s1 = squad[75], s2 = squad[76];
+      int e = 0;
+#pragma unroll
+      for (int j = 0; j < kK0; ++j) {
+        s1 = fmaf(squad[65 + j], xv[j], s1);
+        float row = squad[55 + j];
+#pragma unroll
+        for (int k = j; k < kK0; ++k) row = fmaf(squad[e++], xv[k], row);
+        s2 = fmaf(row, xv[j], s2);
+      }
+      mu = s1 * (1.0f / kC0);
+      rs = rsqrtf(fmaxf(s2 * (1.0f / kC0) - mu * mu, 0.f) + 1e-5f);
+    }
+    // ---- A fragments (hi / lo) of the two 16-frame tiles: taps scaled by the frame's rstd, slot 10 = rstd, slot 11 = -mu rstd
+    uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int fl = 16 * mt + 8 * h + g;            // frame of fragment rows g (h = 0) / g + 8 (h = 1), local index
+        const int f = f0 + fl;
+        const float rs_f = __shfl_sync(0xffffffffu, rs, fl);
+        const float mu_f = __shfl_sync(0xffffffffu, mu, fl);
+        const bool live = f < T;
+        const float* xf = x + kS0 * f;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;     // k = 2 tig, 2 tig + 1, 2 tig + 8, 2 tig + 9
+        if (live) {
+          v0 = fmaf(__ldg(xf + 2 * tig), rstd, in_shift) * rs_f;
+          v1 = fmaf(__ldg(xf + 2 * tig + 1), rstd, in_shift) * rs_f;
+          if (tig == 0) {
+            v2 = fmaf(__ldg(xf + 8), rstd, in_shift) * rs_f;
+            v3 = fmaf(__ldg(xf + 9), rstd, in_shift) * rs_f;
+          } else if (tig == 1) {
+            v2 = rs_f;
+            v3 = -mu_f * rs_f;
+          }
+        }
+        float h0, l0, h1, l1, h2, l2, h3, l3;
+        split_bf16(v0, h0, l0); split_bf16(v1, h1, l1); split_bf16(v2, h2, l2); split_bf16(v3, h3, l3);
+        ahi[mt][h] = pack_bf16x2(h0, h1); ahi[mt][2 + h] = pack_bf16x2(h2, h3);
+        alo[mt][h] = pack_bf16x2(l0, l1); alo[mt][2 + h] = pack_bf16x2(l2, l3);
+      }
+    // ---- 16 groups of four n-tiles = 32 channels; a thread ends up with channels 32 u + 8 tig .. + 7 of its four rows
+#pragma unroll 1
+    for (int u = 0; u < kC0Tiles / 4; ++u) {
+      float acc[2][4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 bf = sfrag[(4 * u + i) * 32 + lane];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma_bf16_16816_zero(acc[mt][i], ahi[mt], bf.x, bf.y);
+          mma_bf16_16816(acc[mt][i], alo[mt], bf.x, bf.y);
+          mma_bf16_16816(acc[mt][i], ahi[mt], bf.z, bf.w);
+        }
+      }
+      const int c0 = 32 * u + 8 * tig;
+      const float4 g0 = *reinterpret_cast<const float4*>(&sgamma[c0]), g1 = *reinterpret_cast<const float4*>(&sgamma[c0 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&sbeta[c0]), b1 = *reinterpret_cast<const float4*>(&sbeta[c0 + 4]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int f = f0 + 16 * mt + 8 * h + g;
+          if (f >= t_alloc) continue;
+          uint4 pk = make_uint4(0u, 0u, 0u, 0u);   // allocation padding rows (f >= T) stay zero
+          if (f < T) {
+            // accumulator registers 2 h, 2 h + 1 of n-tile i are channels c0 + 2 i, c0 + 2 i + 1
+            const float y0 = gelu_erf(fmaf(acc[mt][0][2 * h], g0.x, b0.x)), y1 = gelu_erf(fmaf(acc[mt][0][2 * h + 1], g0.y, b0.y));
+            const float y2 = gelu_erf(fmaf(acc[mt][1][2 * h], g0.z, b0.z)), y3 = gelu_erf(fmaf(acc[mt][1][2 * h + 1], g0.w, b0.w));
+            const float y4 = gelu_erf(fmaf(acc[mt][2][2 * h], g1.x, b1.x)), y5 = gelu_erf(fmaf(acc[mt][2][2 * h + 1], g1.y, b1.y));
+            const float y6 = gelu_erf(fmaf(acc[mt][3][2 * h], g1.z, b1.z)), y7 = gelu_erf(fmaf(acc[mt][3][2 * h + 1], g1.w, b1.w));
+            pk = make_uint4(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3), pack_bf16x2(y4, y5), pack_bf16x2(y6, y7));
+          }
+          *reinterpret_cast<uint4*>(o + static_cast<size_t>(f) * kC0 + c0) = pk;
+        }
+    }
+  }
+}
+
 // group-norm apply + GELU, in place.  block = 256 threads = 4 frames x 64 channel-octets
 __global__ void __launch_bounds__(256)
 groupnorm_gelu_kernel(__nv_bfloat16* __restrict__ x, const double* __restrict__ chan_stats,
@@ -662,13 +859,35 @@ int tensor_stats_per_clip(const float* x, int clips, size_t n_per_clip, double* 
   return kOk;
 }
 
+size_t conv0_tables_bytes() { return kC0FragBytes + sizeof(float) * kC0QuadFloats; }
+int conv0_build_tables(const float* w_kc, const float* bias, void* tables, cudaStream_t stream) {
+  conv0_tables_kernel<<<ceil_div(kC0Tiles * 32, 256), 256, 0, stream>>>(
+      w_kc, bias, static_cast<uint4*>(tables), reinterpret_cast<float*>(static_cast<uint8_t*>(tables) + kC0FragBytes));
+  SVT_POST_LAUNCH();
+  return kOk;
+}
+
 int conv0_forward(const Conv0Args& a, cudaStream_t stream) {
   if (a.C != kC0 || a.k != kK0 || a.stride != kS0)
     return fail(kUnsupported, "conv0: only C=512, kernel=10, stride=5 (every wav2vec2/HuBERT checkpoint) is built");
   if (a.t_alloc % kR0 != 0) return fail(kInvalidArgument, "conv0: t_alloc % 4 != 0");
+  const double n_in = a.stats_stride > 0 ? static_cast<double>(a.L) : static_cast<double>(a.B) * a.L;
+  if (a.layer_mode && a.tc_tables != nullptr && get_option_conv0_impl() != 1) {
+    // tensor-core kernel: a block covers iters x 8 warps x 32 frames; ~5 waves of two blocks per SM
+    const int block_tiles = ceil_div(a.t_alloc, 8 * kC0FramesPerWarp);
+    int iters = ceil_div(block_tiles * a.B, 10 * num_sms());
+    if (iters < 1) iters = 1;
+    if (iters > 8) iters = 8;
+    dim3 grid(ceil_div(block_tiles, iters), a.B);
+    const uint4* frag = static_cast<const uint4*>(a.tc_tables);
+    const float* quad = reinterpret_cast<const float*>(static_cast<const uint8_t*>(a.tc_tables) + kC0FragBytes);
+    conv0_tc_kernel<<<grid, 256, 0, stream>>>(a.wav, a.L, a.T, a.t_alloc, frag, quad, a.gamma, a.beta, a.in_stats, n_in, a.out,
+                                              a.stats_stride, iters);
+    SVT_POST_LAUNCH();
+    return kOk;
+  }
   const int groups = a.t_alloc / kR0;
   dim3 grid(ceil_div(groups, 8 * kConv0GroupsPerWarp), a.B);
-  const double n_in = a.stats_stride > 0 ? static_cast<double>(a.L) : static_cast<double>(a.B) * a.L;
   if (a.layer_mode) {
     conv0_kernel<true><<<grid, 256, 0, stream>>>(a.wav, a.L, a.T, a.t_alloc, a.w, a.bias, a.gamma, a.beta, a.in_stats,
                                                  n_in, a.out, nullptr, a.stats_stride);

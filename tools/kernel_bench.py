@@ -113,6 +113,23 @@ def main():
         gemm("conv1 k3s2 (implicit)", 1024000, 512, 1536, k_inner=512, row_stride=1024, out=out)
         gemm("conv2 k3s2 (implicit)", 512000, 512, 1536, k_inner=512, row_stride=1024, out=out)
         gemm("conv5 k2s2 (implicit)", 64000, 512, 1024, k_inner=512, row_stride=1024, out=out)
+    if "conv0" in which or "conv" in which:
+        Bc, Lc = 64, 160000
+        wav = torch.randn(Bc, Lc, device=dev)
+        w_kc = (torch.randn(10, 512, device=dev) * 0.4).contiguous()
+        bias, gam, bet = torch.randn(512, device=dev) * 0.1, torch.ones(512, device=dev), torch.zeros(512, device=dev)
+        ta = 32000
+        o = torch.empty(Bc, ta, 512, device=dev, dtype=torch.bfloat16)
+        scratch = torch.zeros(4, dtype=torch.float64, device=dev)
+        s_ = current_stream_ptr()
+        for impl in (1, 0):
+            check(lib().svt_set_option(b"conv0_impl", impl))
+            fn = lambda: check(lib().svt_op_conv0(ptr(wav), Bc, Lc, ptr(w_kc), ptr(bias), ptr(gam), ptr(bet), 1, ptr(o), ta, ptr(scratch), s_))
+            us = timeit(fn)
+            nm = "conv0 SIMT (+stats pass)" if impl == 1 else "conv0 mma.sync (+stats, +tables)"
+            print(f"{nm:34s} B={Bc} L={Lc}  {us:9.1f} us  {Bc * ta * 512 * 2 / us / 1e3:7.1f} GB/s written", flush=True)
+            out[nm] = {"us": us}
+        check(lib().svt_set_option(b"conv0_impl", 0))
     if "conv" in which:
         for nm, Mc, Kc in (("conv1", 1024000, 1536), ("conv2", 512000, 1536), ("conv5", 64000, 1024)):
             a = torch.randn(2 * Mc + 8, 512, device=dev).bfloat16()

@@ -21,6 +21,8 @@ static std::atomic<int> g_gemm_impl{0};
 static std::atomic<int> g_ln_fold{1};
 static std::atomic<int> g_rowln_fuse{1};
 static std::atomic<int> g_conv0_impl{0};
+static std::atomic<int> g_resid_bf16{0};
+int get_option_resid_bf16() { return g_resid_bf16.load(std::memory_order_relaxed); }
 int get_option_conv0_impl() { return g_conv0_impl.load(std::memory_order_relaxed); }
 int get_option_ln_fold() { return g_ln_fold.load(std::memory_order_relaxed); }
 int get_option_rowln_fuse() { return g_rowln_fuse.load(std::memory_order_relaxed); }
@@ -63,6 +65,11 @@ int svt_set_option(const char* name, int value) {
   if (n == "ln_fold") {
     if (value < 0 || value > 1) return fail(kInvalidArgument, "ln_fold must be 0 (separate LayerNorm kernels) or 1 (folded)");
     g_ln_fold.store(value);
+    return kOk;
+  }
+  if (n == "resid_bf16") {
+    if (value < 0 || value > 1) return fail(kInvalidArgument, "resid_bf16 must be 0 (fp32 residual stream) or 1 (bf16 only; measurement switch)");
+    g_resid_bf16.store(value);
     return kOk;
   }
   if (n == "conv0_impl") {

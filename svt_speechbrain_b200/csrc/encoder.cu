@@ -433,9 +433,11 @@ EncPlan make_plan(const svt_encoder* e, int B, int L) {
 }
 
 int linear(const __nv_bfloat16* a, int M, const LinearW& w, const float* resid, float* out_f32, __nv_bfloat16* out_bf16,
-           int act, cudaStream_t s, float* row_stats_out = nullptr, const float* ln_stats = nullptr, float ln_eps = 0.f) {
+           int act, cudaStream_t s, float* row_stats_out = nullptr, const float* ln_stats = nullptr, float ln_eps = 0.f,
+           const __nv_bfloat16* resid_bf16 = nullptr) {
   GemmArgs g;
   g.row_stats_out = row_stats_out;
+  g.resid_bf16 = resid_bf16;
   if (ln_stats != nullptr) { g.ln_stats = ln_stats; g.ln_colsum = w.colsum; g.ln_eps = ln_eps; }
   g.a = a;
   g.a_dims[0] = w.K; g.a_dims[1] = 1; g.a_dims[2] = M;
@@ -570,15 +572,29 @@ int encoder_transformer_forward(const svt_encoder* e, int B, int T, int Ta, cons
     float* st = tb.rowstats;                                    // statistics of the rows entering a layer
     float* st_mid = st + 2 * static_cast<size_t>(M) * (D / 128);  // ... and of the rows after the attention block
     SVT_TRY(row_stats_cast(h, M, D, hb, st, s));
+    // Option "resid_bf16" (measurement only, default off): the residual stream lives in its bf16 copy alone -- the two
+    // residual GEMMs read and write 2 instead of 4 + 2 bytes per element -- at the price of one bf16 rounding per residual
+    // add (profiles/r2_resid_bf16_experiment.txt: the logits error doubles, so it is not the default).
+    const bool rb = get_option_resid_bf16() != 0;
     for (int l = 0; l < c.num_layers; ++l) {
       const svt_encoder::Layer& Lw = e->layers[l];
       SVT_TRY(linear(hb, M, Lw.qkv_ln, nullptr, nullptr, qkv, kActNone, s, nullptr, st, eps));
       SVT_TRY(attend(Lw, hb, st));
-      SVT_TRY(linear(ctx, M, Lw.out, h, h, hb, kActNone, s, st_mid));
+      if (rb) SVT_TRY(linear(ctx, M, Lw.out, nullptr, nullptr, hb, kActNone, s, st_mid, nullptr, 0.f, hb));
+      else SVT_TRY(linear(ctx, M, Lw.out, h, h, hb, kActNone, s, st_mid));
       SVT_TRY(linear(hb, M, Lw.ff1_ln, nullptr, nullptr, mid, kActGelu, s, nullptr, st_mid, eps));
-      SVT_TRY(linear(mid, M, Lw.ff2, h, h, hb, kActNone, s, st));
+      if (rb) SVT_TRY(linear(mid, M, Lw.ff2, nullptr, nullptr, hb, kActNone, s, st, nullptr, 0.f, hb));
+      else SVT_TRY(linear(mid, M, Lw.ff2, h, h, hb, kActNone, s, st));
     }
-    SVT_TRY(ln_rows(h, e->enc_norm, nullptr, pre, want_stats ? stats_out : nullptr));
+    if (rb) {
+      LayerNormArgs ln;
+      ln.x_bf16 = hb; ln.gamma = e->enc_norm.g; ln.beta = e->enc_norm.b; ln.y_f32 = pre;
+      ln.rows = M; ln.D = D; ln.eps = eps; ln.stats = want_stats ? stats_out : nullptr; ln.clip_rows = Ta; ln.clip_valid = T;
+      ln.stats_stride = stats_stride;
+      SVT_TRY(layer_norm(ln, s));
+    } else {
+      SVT_TRY(ln_rows(h, e->enc_norm, nullptr, pre, want_stats ? stats_out : nullptr));
+    }
     final_x = pre;
   } else if (c.stable_layer_norm) {
     // pre-LN layers (HF:612-655) + final encoder LN (HF:792)

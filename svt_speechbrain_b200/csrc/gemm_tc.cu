@@ -388,8 +388,8 @@ int gemm_bf16_tc(const GemmArgs& g, cudaStream_t stream) {
     if (g.K % 128 != 0 || g.K / 128 > kMaxLnSlots || g.K / 128 % 2 != 0)
       return fail(kUnsupported, "gemm: a folded LayerNorm needs K in {256, 512, 768, 1024}");
   }
-  if (g.row_stats_out != nullptr && (g.mode != 0 || g.out_f32 == nullptr || g.N % 256 != 0 || g.ld_out != g.N))
-    return fail(kInvalidArgument, "gemm: row statistics need mode 0, an fp32 output and N % 256 == 0 (= ld_out)");
+  if (g.row_stats_out != nullptr && (g.mode != 0 || (g.out_f32 == nullptr && g.resid_bf16 == nullptr) || g.N % 256 != 0 || g.ld_out != g.N))
+    return fail(kInvalidArgument, "gemm: row statistics need mode 0, an fp32 output (or a bf16 residual) and N % 256 == 0 (= ld_out)");
   // Kernel / tile choice.  The CTA-pair kernel (256 x 256 per SM pair) wins whenever there are enough tiles to keep the
   // 74 pairs busy for a few waves; small row counts (a handful of clips) run on the one-CTA kernel with 128-column
   // tiles, which cuts the problem into 4x as many work items.  A producer of LayerNorm statistics needs 256-column

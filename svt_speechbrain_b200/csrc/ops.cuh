@@ -27,6 +27,7 @@ int attention_bf16_tc(const AttentionArgs& a, cudaStream_t stream);    // tcgen0
 // process-wide options (svt_set_option): "attention_impl" 0 = auto, 1 = mma.sync kernel, 2 = tcgen05 kernel
 int get_option_attention_impl();
 int get_option_ln_fold();
+int get_option_resid_bf16();  // "resid_bf16": 1 = bf16-only residual stream in the folded pre-LN layers (measurement switch)
 int get_option_rowln_fuse();  // "rowln_fuse": 1 = LayerNorm(512) + GELU of the conv feature extractor fused into the conv GEMMs
 // development aid: device buffer of 4 x 256 int64 clock stamps written by CTA 0 of the tcgen05 attention kernel
 void set_attention_trace_buffer(long long* dev_ptr);

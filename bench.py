@@ -34,22 +34,33 @@ SAMPLE_RATE = 16000
 
 
 def _ffn1_traffic():
-    """DRAM bytes of one launch of the roofline kernel, from the committed `ncu --set full` capture summary."""
+    """DRAM bytes of one launch of the roofline kernel, from the committed `ncu --set full` capture summary (round 2: the
+    feature extractor + first encoder layer captured inside this bench command, profiles/r2_ncu_full_step_summary.csv)."""
     import csv
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_full_v3_summary.csv")) as f:
-            rows = list(csv.reader(f))
-        h = rows[0]
-        # the capture holds the four GEMMs of one encoder layer; FFN-1 is the one that executes the most instructions
-        # (bias + folded LayerNorm + GELU epilogue over N = 4096 columns)
-        best = max((dict(zip(h, r)) for r in rows[1:] if "gemm_tc2" in r[1]), key=lambda d: float(d["smsp__inst_executed.sum [inst]"]))
-        return int((float(best["dram__bytes_read.sum [Mbyte]"]) + float(best["dram__bytes_write.sum [Mbyte]"])) * 1e6)
-    except Exception:
-        pass
-    return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for name in ("r2_ncu_full_step_summary.csv", "r1_ncu_full_v3_summary.csv"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                rows = list(csv.reader(f))
+            h = rows[0]
+            col = {k.split(" [")[0]: (i, (k.split(" [")[1][:-1] if " [" in k else "")) for i, k in enumerate(h)}
+            # FFN-1 is the GEMM that executes the most XU (MUFU) work per launch among the transformer GEMMs: bias + folded
+            # LayerNorm + GELU epilogue over N = 4096 columns; the conv GEMMs of the feature extractor come earlier in the list
+            gemms = [r for r in rows[1:] if "gemm_tc2" in r[1]]
+            if name.startswith("r2"):
+                gemms = gemms[-4:]  # qkv, out-proj, FFN-1, FFN-2 of the first encoder layer
+            best = max(gemms, key=lambda r: float(r[col["smsp__inst_executed.sum"][0]]))
+            tot = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i, unit = col[k]
+                tot += float(best[i]) * scale[unit]
+            return int(tot), name
+        except Exception:
+            continue
+    return None, None
 
 
-FFN1_DRAM_BYTES = _ffn1_traffic()
+FFN1_DRAM_BYTES, FFN1_DRAM_SRC = _ffn1_traffic()
 
 
 def _peaks():
@@ -443,7 +454,7 @@ def run_ours(args):
         roof = {"bound": "tensor", "kernel": "gemm_tc2_kernel, CTA-pair tcgen05 GEMM (FFN-1 of the step: M=%d N=%d K=%d, folded LayerNorm + bias + GELU epilogue)" % (M, N, K),
                 "achieved": tf, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": tf / peaks["bf16"], "traffic": FFN1_DRAM_BYTES,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full, "
-                                  "profiles/r1_ncu_full_v3_summary.csv (algorithmic: A 65.5 MB + W 8.4 MB + row statistics 2 MB + out 262.1 MB)",
+                                  f"profiles/{FFN1_DRAM_SRC} (algorithmic: A 65.5 MB + W 8.4 MB + row statistics 2 MB + out 262.1 MB)",
                 "peak_source": peaks["src"] + " burst (kernel timed alone)", "us_per_launch": t_ms * 1e3,
                 "whole_step": {"achieved": step_tf, "peak": peaks["bf16_sustained"], "frac": step_tf / peaks["bf16_sustained"],
                                "frac_of_burst": step_tf / peaks["bf16"],

@@ -89,6 +89,18 @@ def main():
     if "gemm" in which:
         gemm("qkv (bf16 out)", M, 3072, 1024, out=out)
         gemm("out-proj (+resid fp32)", M, 1024, 1024, resid=True, out=out)
+        for nm, (N_, K_) in {"out-proj (+resid fp32, +bf16 copy, +row stats)": (1024, 1024), "ffn2 (+resid fp32, +bf16 copy, +row stats)": (1024, 4096)}.items():
+            a = torch.randn(M, K_, device=dev).bfloat16()
+            w = (torch.randn(N_, K_, device=dev) * 0.03).bfloat16()
+            bias = torch.zeros(N_, device=dev)
+            h = torch.randn(M, N_, device=dev)
+            hb = torch.empty(M, N_, device=dev, dtype=torch.bfloat16)
+            st = torch.empty(M, N_ // 128, 2, device=dev)
+            s_ = current_stream_ptr()
+            fn = lambda: check(lib().svt_op_gemm_ln(ptr(a), ptr(w), ptr(bias), None, None, 1e-5, ptr(st), ptr(h), ptr(h), ptr(hb), M, N_, K_, 0, s_))
+            us = timeit(fn)
+            print(f"{nm:34s} M={M:8d} N={N_:5d} K={K_:5d}  {us:9.1f} us  {2.0 * M * N_ * K_ / us / 1e6:7.1f} TFLOP/s", flush=True)
+            out[nm] = {"us": us}
         gemm("ffn1 (gelu, bf16 out)", M, 4096, 1024, act=1, out=out)
         gemm("ffn2 (+resid fp32)", M, 1024, 4096, resid=True, out=out)
         if "variants" in which:

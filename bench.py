@@ -161,7 +161,8 @@ def cpu_reference_throughput(n_timed: int, warmup: int, large: bool = True):
 def workload_config(B, world, T):
     """The `config` object of both arms (BASELINE config 2; at N GPUs config 3's weak scaling)."""
     return {"workload": f"wav2vec2-large AMT encoder+head (random init), {B} x 10-s 16 kHz clips per GPU per step "
-                        f"(BASELINE config 2; N=8 -> config 3's 512 clips), logits all-gathered over NCCL when N>1",
+                        f"(BASELINE config 2; N=8 -> config 3's 512 clips; at N>1 the {B * world} clips of a step are sharded in "
+                        f"proportion to each GPU's measured speed, see multi_gpu), logits all-gathered over NCCL when N>1",
             "global_batch": B * world, "frames_per_clip": T, "parallelism": f"dp{world}",
             "l2": "inputs rotate over 4 x 41 MB buffers (> 126 MB L2) and each step streams > 3 GB of activations"}
 
@@ -242,13 +243,14 @@ def run_ours(args):
     # 4 rotating input batches (4 x 41 MB > 126 MB L2): inputs are never L2-resident; the step itself streams
     # > 3 GB of activations through HBM, so nothing survives in L2 from one step to the next either.
     gen = torch.Generator(device=dev).manual_seed(1986 + rank)
-    wavs = [torch.randn(B, L, device=dev, generator=gen) for _ in range(4)]
-    gat = LogitsGatherer((B, T, 20), depth=2, device=dev)
+    state = {"B": B, "wavs": [torch.randn(B, L, device=dev, generator=gen) for _ in range(4)],
+             "gat": LogitsGatherer((B, T, 20), depth=2, device=dev)}
 
     def step(i, gather=True):
         # forward of step i writes into slot i % 2; its all-gather is asynchronous (own NCCL stream), so the forward of
         # step i + 1 is queued behind this one without waiting for the collective
-        eng.forward(wavs[i % 4], want_feats=False, want_logits=True, logits_out=gat.local(i))
+        gat = state["gat"]
+        eng.forward(state["wavs"][i % 4], want_feats=False, want_logits=True, logits_out=gat.local(i, state["B"]))
         if gather:
             gat.submit(i)
 
@@ -264,7 +266,7 @@ def run_ours(args):
         e0.record()
         for i in range(n):
             step(i, gather)
-        gat.finish()  # the last gathers are part of the timed work
+        state["gat"].finish()  # the last gathers are part of the timed work
         e1.record()
         barrier()
         return e0.elapsed_time(e1), t0, time.time()
@@ -280,8 +282,44 @@ def run_ours(args):
 
     for i in range(args.warmup):
         step(i)
-    gat.finish()
+    state["gat"].finish()
     barrier()
+
+    # ---- N > 1: the GPUs of one box do not run at one speed under the power cap, and a step that gathers its logits runs at
+    # the pace of the slowest.  Every rank times its own forward on the even split (also reported: `equal_split`), then the
+    # N x B clips of a step are re-sharded in proportion to the measured speeds (parallel.balanced_shares); the global batch,
+    # the gather and the timing rules are unchanged.
+    multi = None
+    shares = [B] * world
+    if world > 1:
+        ms_eq, _, _ = timed(args.steps)
+        ms_eq, per_rank_eq = max_over_ranks(ms_eq)
+        ms_ng, _, _ = timed(args.steps, gather=False)
+        ms_ng, per_rank_ng = max_over_ranks(ms_ng)
+        multi = {"equal_split": {"ms_per_step": ms_eq / args.steps, "value": world * B * CLIP_SECONDS / (ms_eq / args.steps * 1e-3),
+                                 "per_rank_ms_per_step": [v / args.steps for v in per_rank_eq],
+                                 "without_gather": {"ms_per_step": ms_ng / args.steps,
+                                                    "per_rank_ms_per_step": [v / args.steps for v in per_rank_ng]}},
+                 "gather": "ncclAllGather (all_gather_into_tensor) of the per-rank (share, T, 20) fp32 logits into pre-allocated "
+                           "double-buffered (N * max share, T, 20) tensors, asynchronous on the NCCL stream, drained when the slot is "
+                           "reused / at the end"}
+        if not args.no_balance:
+            from svt_speechbrain_b200.parallel import balanced_shares
+            shares = balanced_shares(world * B, per_rank_ng)
+            state["B"] = shares[rank]
+            state["wavs"] = [torch.randn(shares[rank], L, device=dev, generator=gen) for _ in range(4)]
+            state["gat"] = LogitsGatherer((max(shares), T, 20), depth=2, device=dev)
+            for i in range(max(3, args.warmup)):
+                step(i)
+            state["gat"].finish()
+            barrier()
+        multi["shares"] = shares
+        multi["sharding"] = ("clips of a step sharded in proportion to each GPU's measured speed" if not args.no_balance
+                             else "even split")
+    Bl = state["B"]
+    gat = state["gat"]
+    wavs = state["wavs"]
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -294,16 +332,10 @@ def run_ours(args):
     ms_per_step = ms_total / args.steps
     value = world * B * CLIP_SECONDS / (ms_per_step * 1e-3)
     last_slot = (args.steps - 1) % gat.depth
-    last_logits = gat._local[last_slot].clone()       # this rank's logits of the last timed step
+    last_logits = gat._local[last_slot][:Bl].clone()       # this rank's logits of the last timed step
     last_wav = wavs[(args.steps - 1) % 4]
-    multi = None
-    if world > 1:
-        ms_ng, _, _ = timed(args.steps, gather=False)
-        ms_ng, per_rank_ng = max_over_ranks(ms_ng)
-        multi = {"per_rank_ms_per_step": [v / args.steps for v in per_rank_ms],
-                 "without_gather": {"ms_per_step": ms_ng / args.steps, "per_rank_ms_per_step": [v / args.steps for v in per_rank_ng]},
-                 "gather": "ncclAllGather (all_gather_into_tensor) of the (B, T, 20) fp32 logits into pre-allocated double-buffered "
-                           "(N*B, T, 20) tensors, asynchronous on the NCCL stream, drained when the slot is reused / at the end"}
+    if multi is not None:
+        multi["per_rank_ms_per_step"] = [v / args.steps for v in per_rank_ms]
 
     # ---- parity of the timed shape, outside the timed region: the last timed step's logits of three clips against the fp32
     # oracle evaluating ONE batched reference call clip by clip (input statistics over the whole batch; output statistics
@@ -311,12 +343,12 @@ def run_ours(args):
     # of the final features has mean 0 and the same variance).
     parity = None
     if rank == 0 and not args.no_parity:
-        clips = [c for c in PARITY_CLIPS if c < B]
+        clips = sorted({min(c, Bl - 1) for c in PARITY_CLIPS})
         with torch.no_grad():
             ref = wo.amt_logits_of_clips(cfg, sd, head, last_wav.cpu(), clips=clips, stat_clips=clips)
         got = last_logits[clips].cpu()
         parity = {"rel_l2": float((got - ref).norm() / ref.norm()), "max_abs": float((got - ref).abs().max()),
-                  "clips": clips, "shape": [B, L], "tolerance": {"rel_l2": 2e-2, "max_abs": 0.1},
+                  "clips": clips, "shape": [Bl, L], "tolerance": {"rel_l2": 2e-2, "max_abs": 0.1},
                   "against": "fp32 CPU oracle (oracle/wav2vec2_oracle.py, pinned to the reference's own output at this shape by "
                              "tests/golden/w2v2_large_10s_b64.npz), logits of the LAST TIMED STEP"}
         parity["ok"] = bool(parity["rel_l2"] <= 2e-2 and parity["max_abs"] <= 0.1)
@@ -326,7 +358,7 @@ def run_ours(args):
     # device and its logits back to pinned host memory; two batches in flight, the copy of step k + 1 runs under the
     # forward of step k.  N > 1: the same with the all-gather of the step's logits INSIDE the loop -- pinned host wav ->
     # H2D (copy stream) -> forward -> async all-gather -> D2H of the gathered (N*B, T, 20) logits on every rank.
-    wav_host = [torch.randn(B, L, generator=torch.Generator().manual_seed(7 + i)).pin_memory() for i in range(2)]
+    wav_host = [torch.randn(Bl, L, generator=torch.Generator().manual_seed(7 + i)).pin_memory() for i in range(2)]
     n_e2e = max(2, args.steps)
     e2e_s, e2e_api, d2h = float("nan"), "skipped (--no-e2e)", 0
     if args.no_e2e:
@@ -355,8 +387,8 @@ def run_ours(args):
         e2e_api = "svt_pipeline_submit / svt_pipeline_wait, depth 2 (pinned host wav -> H2D -> forward -> D2H pinned host logits, every step)"
         d2h = B * T * 20 * 4
     else:
-        gathered_host = [torch.empty(world * B, T, 20).pin_memory() for _ in range(2)]
-        wav_dev = [torch.empty(B, L, device=dev) for _ in range(2)]
+        gathered_host = [torch.empty(world * max(shares), T, 20).pin_memory() for _ in range(2)]
+        wav_dev = [torch.empty(Bl, L, device=dev) for _ in range(2)]
         copy_s = torch.cuda.Stream(device=dev)
         main_s = torch.cuda.current_stream(dev)
         h2d_done = [torch.cuda.Event() for _ in range(2)]
@@ -373,7 +405,7 @@ def run_ours(args):
                         wav_dev[s].copy_(wav_host[s], non_blocking=True)
                         h2d_done[s].record(copy_s)
                     main_s.wait_event(h2d_done[s])
-                    eng.forward(wav_dev[s], want_feats=False, want_logits=True, logits_out=gat.local(i))
+                    eng.forward(wav_dev[s], want_feats=False, want_logits=True, logits_out=gat.local(i, Bl))
                     fwd_done[s].record(main_s)
                     gat.submit(i)
                 if i >= 1:                                     # consume step i - 1: gathered logits -> pinned host
@@ -393,22 +425,22 @@ def run_ours(args):
         e2e_s = (time.perf_counter() - t0) / n_e2e
         e2e_api = ("pinned host wav -> H2D (copy stream) -> EncoderEngine.forward -> asynchronous NCCL all-gather of the logits -> "
                    "D2H of the gathered (N*B, T, 20) logits to pinned host memory on every rank, double-buffered")
-        d2h = world * B * T * 20 * 4
+        d2h = world * max(shares) * T * 20 * 4
     if not args.no_e2e:
         e2e_s, _ = max_over_ranks(e2e_s)
     e2e_value = world * B * CLIP_SECONDS / e2e_s
 
     # ---- e2e #2, where the CPU arm ends: wav on the HOST -> notes on the HOST through AMTTranscriber.transcribe_songs (the
     # evaluation driver: H2D, batched per-clip-norm forward, one argmax pass + one D2H, host sigmoid + frame2note per song).
-    songs_host = [wav_host[0][c] for c in range(B if not args.no_e2e else 1)]
+    songs_host = [wav_host[0][c] for c in range(Bl if not args.no_e2e else 1)]
     for _ in range(2):
-        notes = tr.transcribe_songs(songs_host, dur=float(CLIP_SECONDS), batch_clips=B)
+        notes = tr.transcribe_songs(songs_host, dur=float(CLIP_SECONDS), batch_clips=max(shares))
     n_notes_runs = max(3, min(args.steps, 7))
     call_s = []
     barrier()
     for _ in range(n_notes_runs):
         t0 = time.perf_counter()
-        notes = tr.transcribe_songs(songs_host, dur=float(CLIP_SECONDS), batch_clips=B)   # returns with the notes on the host
+        notes = tr.transcribe_songs(songs_host, dur=float(CLIP_SECONDS), batch_clips=max(shares))   # returns with the notes on the host
         call_s.append(time.perf_counter() - t0)
     barrier()
     call_s.sort()
@@ -483,7 +515,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(B, world, T),
-            "e2e": {"value": e2e_value, "unit": "audio-sec/sec", "h2d_bytes_per_step": B * L * 4,
+            "e2e": {"value": e2e_value, "unit": "audio-sec/sec", "h2d_bytes_per_step": Bl * L * 4,
                     "d2h_bytes_per_step": d2h, "api": e2e_api, "gather_included": world > 1},
             "e2e_notes": e2e_notes,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "parity": parity,
@@ -597,6 +629,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the config 4 (audio-visual) and config 5 (long-form) legs")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: keep the even split of clips over the ranks")
     ap.add_argument("--no-e2e", action="store_true", help="development: skip the host-buffer legs (tools/ab_step.py)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the last timed step's logits")
     ap.add_argument("--av-clips", type=int, default=4, help="clips per GPU of the audio-visual leg (config 4: 32 / 8 GPUs)")

@@ -85,3 +85,21 @@ def test_double_buffered_gatherer_and_even_gather():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res), res
+
+
+def test_balanced_shares_apportionment():
+    """Speed-proportional sharding of a step's clips (bench.py at N > 1): shares sum to the total, follow the measured
+    speeds, never drop a rank, and make the slowest rank's step shorter than the even split does."""
+    from svt_speechbrain_b200.parallel import balanced_shares
+
+    t = [26.22, 25.99, 26.11, 25.47, 27.58, 26.86, 27.72, 26.90]   # ms per 64 clips on the 8 GPUs of one box (round-2 run)
+    s = balanced_shares(512, t)
+    assert sum(s) == 512 and min(s) >= 1
+    assert s[3] == max(s) and s[6] == min(s)                        # fastest GPU gets the most clips, slowest the fewest
+    assert max(a * b / 64 for a, b in zip(s, t)) < max(t) - 0.5     # the step no longer runs at the slowest GPU's pace
+    assert balanced_shares(128, [1.0, 1.0]) == [64, 64]
+    assert balanced_shares(7, [1.0, 1.0]) in ([4, 3], [3, 4])
+    assert balanced_shares(3, [1.0, 100.0, 100.0]) == [1, 1, 1]
+    assert balanced_shares(5, [1.0, 100.0, 100.0]) == [3, 1, 1]
+    s = balanced_shares(10, [1.0, 1000.0])
+    assert sum(s) == 10 and s[1] >= 1

@@ -219,24 +219,13 @@ class AMTTranscriber:
         following batches."""
         hp = self.hp
         songs = [w.to(self.device, torch.float32, non_blocking=True).reshape(-1) for w in wavs]
-        jobs = []  # (length, song, utterance index, start, stop)
-        n_utt = []
-        for si, w in enumerate(songs):
-            spans = split_song(w.numel(), hp, dur)
-            n_utt.append(len(spans))
-            for ui, (a, b) in enumerate(spans):
-                jobs.append((b - a, si, ui, a, b))
-        jobs.sort(key=lambda t: (t[0], t[1], t[2]))  # equal lengths become neighbours
+        n_utt, plan = plan_song_batches([w.numel() for w in songs], hp, dur, batch_clips)
         stream = torch.cuda.current_stream(self.device)
         batches = []  # (pinned (frames, 4) tensor, event, [(song, utt, first row, rows)])
-        i = 0
-        while i < len(jobs):
-            j = i
-            while j < len(jobs) and j - i < batch_clips and jobs[j][0] == jobs[i][0]:
-                j += 1
-            lgs = self._clip_logits([songs[si][a:b] for _, si, _, a, b in jobs[i:j]], batch_clips, per_clip_norm)
+        for jobs in plan:
+            lgs = self._clip_logits([songs[si][a:b] for si, _, a, b in jobs], batch_clips, per_clip_norm)
             rows, index = 0, []
-            for (_, si, ui, _, _), lg in zip(jobs[i:j], lgs):
+            for (si, ui, _, _), lg in zip(jobs, lgs):
                 index.append((si, ui, rows, int(lg.shape[0])))
                 rows += int(lg.shape[0])
             packed = _pack_frames(torch.cat(lgs, dim=0) if len(lgs) > 1 else lgs[0], hp)
@@ -245,7 +234,6 @@ class AMTTranscriber:
             ev = torch.cuda.Event()
             ev.record(stream)
             batches.append((host, ev, index))
-            i = j
         pieces = {}
         done = [0] * len(songs)
         results: List[Optional[np.ndarray]] = [None] * len(songs)
@@ -289,6 +277,28 @@ def _unpack_frames(packed_host: torch.Tensor):
     ids = packed_host[:, 2:].contiguous().view(torch.int32)
     return (p[:, 0].contiguous().numpy(), p[:, 1].contiguous().numpy(), ids[:, 0].contiguous().numpy(),
             ids[:, 1].contiguous().numpy())
+
+
+def plan_song_batches(n_samples: Sequence[int], hp: "AMTHparams", dur: Optional[float], batch_clips: int):
+    """Host-side plan of the evaluation driver: every song is cut into utterances by the reference rule (split_song), the
+    utterances of ALL songs are sorted by length so that equal lengths become neighbours, and runs of equal length are cut
+    into batches of at most `batch_clips`.  Returns (utterances per song, [batch, ...]) with batch = [(song, utterance index,
+    first sample, end sample), ...]; every utterance appears in exactly one batch."""
+    jobs, n_utt = [], []
+    for si, n in enumerate(n_samples):
+        spans = split_song(n, hp, dur)
+        n_utt.append(len(spans))
+        for ui, (a, b) in enumerate(spans):
+            jobs.append((b - a, si, ui, a, b))
+    jobs.sort(key=lambda t: (t[0], t[1], t[2]))
+    plan, i = [], 0
+    while i < len(jobs):
+        j = i
+        while j < len(jobs) and j - i < batch_clips and jobs[j][0] == jobs[i][0]:
+            j += 1
+        plan.append([(si, ui, a, b) for _, si, ui, a, b in jobs[i:j]])
+        i = j
+    return n_utt, plan
 
 
 def decode_logits_many(per_song: Sequence[torch.Tensor], hp: "AMTHparams") -> List[np.ndarray]:

@@ -88,3 +88,24 @@ def test_tail_shorter_than_one_frame_is_merged_into_the_last_window():
         assert a // FRAME_HOP + lo == g
         g = a // FRAME_HOP + hi
     assert g == (n - FRAME_FIELD) // FRAME_HOP + 1
+
+
+def test_evaluation_driver_batch_plan():
+    """plan_song_batches (the host half of AMTTranscriber.transcribe_songs): every utterance of every song exactly once,
+    batches hold one clip length each and at most batch_clips clips, utterances follow the reference chunk rule."""
+    from svt_speechbrain_b200.amt import AMTHparams, plan_song_batches, split_song
+
+    hp = AMTHparams()  # 5-s utterances
+    lengths = [16000 * 12 + 1234, 16000 * 5, 16000 * 30, 16000 * 7 + 3, 16000 * 10]
+    n_utt, plan = plan_song_batches(lengths, hp, None, batch_clips=4)
+    assert n_utt == [len(split_song(n, hp)) for n in lengths]
+    seen = set()
+    for batch in plan:
+        assert 1 <= len(batch) <= 4
+        assert len({b - a for _, _, a, b in batch}) == 1
+        for si, ui, a, b in batch:
+            assert (si, ui) not in seen and split_song(lengths[si], hp)[ui] == (a, b)
+            seen.add((si, ui))
+    assert seen == {(si, ui) for si, k in enumerate(n_utt) for ui in range(k)}
+    # 80 000-sample utterances: 1 (song 0) + 1 (song 1) + 6 (song 2) + 2 (song 4) = 10 -> batches of 4, 4, 2
+    assert sorted(len(b) for b in plan if b[0][3] - b[0][2] == 80000) == [2, 4, 4]

@@ -22,6 +22,8 @@ static std::atomic<int> g_ln_fold{1};
 static std::atomic<int> g_rowln_fuse{1};
 static std::atomic<int> g_conv0_impl{0};
 static std::atomic<int> g_resid_bf16{0};
+static std::atomic<int> g_resid_epilogue{1};
+int get_option_resid_epilogue() { return g_resid_epilogue.load(std::memory_order_relaxed); }
 int get_option_resid_bf16() { return g_resid_bf16.load(std::memory_order_relaxed); }
 int get_option_conv0_impl() { return g_conv0_impl.load(std::memory_order_relaxed); }
 int get_option_ln_fold() { return g_ln_fold.load(std::memory_order_relaxed); }
@@ -65,6 +67,11 @@ int svt_set_option(const char* name, int value) {
   if (n == "ln_fold") {
     if (value < 0 || value > 1) return fail(kInvalidArgument, "ln_fold must be 0 (separate LayerNorm kernels) or 1 (folded)");
     g_ln_fold.store(value);
+    return kOk;
+  }
+  if (n == "resid_epilogue") {
+    if (value < 0 || value > 1) return fail(kInvalidArgument, "resid_epilogue must be 0 (generic fp32 epilogue) or 1 (specialised residual epilogue)");
+    g_resid_epilogue.store(value);
     return kOk;
   }
   if (n == "resid_bf16") {

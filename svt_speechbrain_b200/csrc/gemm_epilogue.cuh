@@ -100,7 +100,7 @@ __device__ __forceinline__ GemmEpiPrefetch gemm_epi_prefetch(const GemmEpiParams
 //   fp32 / residual   : raw accumulators through 4 KB of staging, then bias, activation and the fp32 residual
 //                       (prefetched ahead of the TMEM read) in the coalesced mapping, where a lane keeps the
 //                       same 4 columns for all 8 of its rows.
-template <int BN>
+template <int BN, int kMode = 0>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int row0, int valid, int col0, int n_valid,
                                                    uint32_t tmem_acc, int quad, int half, int lane, uint32_t stage_addr,
                                                    const GemmEpiPrefetch& pf, float2* row_sums = nullptr) {
@@ -147,8 +147,63 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
     *col = col0 + col_in_tile;
     *nv = n_valid - col_in_tile;  // valid columns of this 32-wide chunk
   };
-  if (f32_path) {
-    // fp32 / residual outputs: HBM-bound epilogues; one register array, copied once per chunk
+  // kMode = 1 (own kernel instantiation, chosen on the host by gemm_epi_resid_fast): the residual GEMMs of the transformer
+  // layers -- bias + fp32 residual in place + bf16 copy + row statistics over whole 256-column tiles.  Same order of memory
+  // operations as the generic path below (the chunk's eight residual loads in one burst ahead of the TMEM wait), but the
+  // pointers and row predicates are formed once per tile, the accumulators go to the staging tile straight from the TMEM
+  // registers and none of the other variants' branches are compiled in: the generic path spends ~29 instructions per
+  // element at a per-warp IPC of 0.14, and that, not HBM, paces the out-projection (profiles/r2_rejected_experiments.txt).
+  if constexpr (kMode == 1) {
+    const int rbase = quad * 32 + (lane >> 3);
+    uint32_t vmask = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) vmask |= (rbase + 4 * i < valid) ? (1u << i) : 0u;
+    const size_t ld = static_cast<size_t>(p.ld_out);
+    const size_t base = static_cast<size_t>(row0 + rbase) * ld + static_cast<size_t>(col0 + half * kColsPerWarp + 4 * c4);
+    const float* rp = p.resid + base;
+    float* of = p.out_f32 + base;
+    __nv_bfloat16* ob = p.out_bf16 + base;
+    const float* bp = p.bias + col0 + half * kColsPerWarp + 4 * c4;
+    const size_t step = 4 * ld;
+    const bool want_stats = p.row_stats_out != nullptr;
+    uint32_t rn[32];
+    tmem_ld32(tmem_row, rn);
+#pragma unroll 1
+    for (int c = 0; c < kColsPerWarp; c += 32) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + c));
+      float4 rs[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        rs[i] = ((vmask >> i) & 1u) ? *reinterpret_cast<const float4*>(rp + i * step + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      tmem_ld_wait_regs(rn);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        epi_sts128(stage_addr + lane * 128 + ((q ^ (lane & 7)) << 4), rn[4 * q], rn[4 * q + 1], rn[4 * q + 2], rn[4 * q + 3]);
+      if (c + 32 < kColsPerWarp) tmem_ld32(tmem_row + c + 32, rn);
+      __syncwarp();
+      uint4 raw[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + (lane >> 3);
+        raw[i] = epi_lds128(stage_addr + rr * 128 + ((c4 ^ (rr & 7)) << 4));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = make_float4(__uint_as_float(raw[i].x) + b4.x + rs[i].x, __uint_as_float(raw[i].y) + b4.y + rs[i].y,
+                                     __uint_as_float(raw[i].z) + b4.z + rs[i].z, __uint_as_float(raw[i].w) + b4.w + rs[i].w);
+        if ((vmask >> i) & 1u) {
+          if (want_stats) {
+            ps[i] += (a.x + a.y) + (a.z + a.w);
+            pss[i] = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, pss[i]))));
+          }
+          *reinterpret_cast<float4*>(of + i * step + c) = a;
+          *reinterpret_cast<uint2*>(ob + i * step + c) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+        }
+      }
+      __syncwarp();
+    }
+  } else if (f32_path) {
+    // fp32 / residual outputs: one register array, copied once per chunk
     uint32_t rn[32];
     tmem_ld32(tmem_row, rn);
 #pragma unroll 1
@@ -333,6 +388,14 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
   }
 }
 #endif  // __CUDACC__
+
+// the residual GEMMs of the transformer layers qualify for the specialised epilogue (kMode = 1)
+inline bool gemm_epi_resid_fast(const GemmEpiParams& p, int N) {
+  return N % 256 == 0 && p.resid != nullptr && p.out_f32 != nullptr && p.out_bf16 != nullptr && p.resid_bf16 == nullptr &&
+         p.row_mask == nullptr && p.act == kActNone && p.bias != nullptr && p.ln_stats == nullptr && p.rowln_gamma == nullptr;
+}
+// process-wide option "resid_epilogue": 1 (default) = specialised epilogue kernel for the residual GEMMs, 0 = generic path
+int get_option_resid_epilogue();
 
 // CTA-pair (cta_group::2) kernel, gemm_tc2.cu
 bool gemm_pair_supported(const GemmArgs& g);

@@ -166,6 +166,8 @@ __device__ __forceinline__ void rowln_finish(const GemmEpiParams& p, int row0, i
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// kEpi: 0 = every epilogue variant, 1 = only the residual path of gemm_epilogue_tile (out-projection / FFN-2)
+template <int kEpi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmEpiParams p,
                 int k_inner, int num_kb, int m_pairs, int n_tiles, int n_inner) {
@@ -330,8 +332,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
         float2 rs = make_float2(0.f, 0.f);
-        gemm_epilogue_tile<BN2>(p, row0, valid, col0, BN2, tmem_base + static_cast<uint32_t>(as * BN2), quad, half, lane,
-                                stage_mine, pf_cur, rowln ? &rs : nullptr);
+        gemm_epilogue_tile<BN2, kEpi>(p, row0, valid, col0, BN2, tmem_base + static_cast<uint32_t>(as * BN2), quad, half, lane,
+                                      stage_mine, pf_cur, rowln ? &rs : nullptr);
         // all of this warp's TMEM reads are complete -> release the accumulator stage to the leader's MMA thread
         tc_fence_before();
         __syncwarp();
@@ -395,13 +397,19 @@ int gemm_bf16_tc_pair(const GemmArgs& g, cudaStream_t stream) {
   const uint32_t wb[2] = {BK, BN2 / 2};
   SVT_TRY(encode_bf16_map(&tmB, g.w, 2, wd, ws, wb));
   static std::atomic<unsigned long long> attr_seen{0};
-  if (first_use_on_device(attr_seen)) SVT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+  if (first_use_on_device(attr_seen)) {
+    SVT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+    SVT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+  }
   const int m_pairs = ceil_div(g.M, 2 * BM);
   const int n_tiles = g.N / BN2;
   const int units = m_pairs * n_tiles / n_inner;
   const int max_pairs = num_sms() / 2;
   const int grid = 2 * (units < max_pairs ? units : max_pairs);
-  gemm_tc2_kernel<<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles, n_inner);
+  if (gemm_epi_resid_fast(p, g.N) && get_option_resid_epilogue() != 0)
+    gemm_tc2_kernel<1><<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles, n_inner);
+  else
+    gemm_tc2_kernel<0><<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles, n_inner);
   SVT_POST_LAUNCH();
   return kOk;
 }

@@ -22,7 +22,7 @@ static std::atomic<int> g_ln_fold{1};
 static std::atomic<int> g_rowln_fuse{1};
 static std::atomic<int> g_conv0_impl{0};
 static std::atomic<int> g_resid_bf16{0};
-static std::atomic<int> g_resid_epilogue{1};
+static std::atomic<int> g_resid_epilogue{2};
 int get_option_resid_epilogue() { return g_resid_epilogue.load(std::memory_order_relaxed); }
 int get_option_resid_bf16() { return g_resid_bf16.load(std::memory_order_relaxed); }
 int get_option_conv0_impl() { return g_conv0_impl.load(std::memory_order_relaxed); }
@@ -70,7 +70,8 @@ int svt_set_option(const char* name, int value) {
     return kOk;
   }
   if (n == "resid_epilogue") {
-    if (value < 0 || value > 1) return fail(kInvalidArgument, "resid_epilogue must be 0 (generic fp32 epilogue) or 1 (specialised residual epilogue)");
+    if (value < 0 || value > 2)
+      return fail(kInvalidArgument, "resid_epilogue must be 0 (generic epilogue kernel), 1 (+ specialised residual epilogue) or 2 (+ specialised QKV / FFN-1 epilogues)");
     g_resid_epilogue.store(value);
     return kOk;
   }

@@ -105,11 +105,15 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
                                                    uint32_t tmem_acc, int quad, int half, int lane, uint32_t stage_addr,
                                                    const GemmEpiPrefetch& pf, float2* row_sums = nullptr) {
   constexpr int kColsPerWarp = BN / 2;
-  const bool f32_path = (p.out_f32 != nullptr || p.resid != nullptr || p.resid_bf16 != nullptr || p.row_mask != nullptr ||
-                         p.act == kActPRelu);
+  // kMode 2 / 3 (own kernel instantiations, gemm_epi_mode() on the host): bf16-only output with the folded LayerNorm and
+  // GELU (FFN-1) / no activation (QKV) known at compile time -- no runtime switches in the 32-element chunk body.
+  constexpr bool kFixedBf16 = kMode == 2 || kMode == 3;
+  const bool f32_path = !kFixedBf16 && (p.out_f32 != nullptr || p.resid != nullptr || p.resid_bf16 != nullptr ||
+                                        p.row_mask != nullptr || p.act == kActPRelu);
+  const int act = kMode == 2 ? static_cast<int>(kActGelu) : (kMode == 3 ? static_cast<int>(kActNone) : p.act);
   const int c4 = lane & 7;
   const uint32_t bias_slot = stage_addr + 2048, colsum_slot = stage_addr + 2048 + 512;
-  const bool ln = p.ln_stats != nullptr;  // host side guarantees !f32_path and bias != nullptr with it
+  const bool ln = kFixedBf16 || p.ln_stats != nullptr;  // host side guarantees !f32_path and bias != nullptr with it
   float ln_rstd = 1.f, ln_shift = 0.f;
   if (!f32_path && p.bias != nullptr) {
     if (4 * lane < kColsPerWarp) {
@@ -329,10 +333,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
         }
         rsum += s0 + s1; rsq += q0 + q1;
       }
-      if (p.act == kActGelu) {
+      if (act == kActGelu) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-      } else if (p.act == kActRelu) {
+      } else if (act == kActRelu) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
       }
@@ -394,7 +398,18 @@ inline bool gemm_epi_resid_fast(const GemmEpiParams& p, int N) {
   return N % 256 == 0 && p.resid != nullptr && p.out_f32 != nullptr && p.out_bf16 != nullptr && p.resid_bf16 == nullptr &&
          p.row_mask == nullptr && p.act == kActNone && p.bias != nullptr && p.ln_stats == nullptr && p.rowln_gamma == nullptr;
 }
-// process-wide option "resid_epilogue": 1 (default) = specialised epilogue kernel for the residual GEMMs, 0 = generic path
+// epilogue variant of a CTA-pair launch: 1 residual GEMM, 2 folded LayerNorm + GELU (FFN-1), 3 folded LayerNorm (QKV), 0 generic
+inline int gemm_epi_mode(const GemmEpiParams& p, int N) {
+  if (gemm_epi_resid_fast(p, N)) return 1;
+  const bool bf16_ln = p.ln_stats != nullptr && p.bias != nullptr && p.ln_colsum != nullptr && p.out_bf16 != nullptr &&
+                       p.out_f32 == nullptr && p.resid == nullptr && p.resid_bf16 == nullptr && p.row_mask == nullptr &&
+                       p.rowln_gamma == nullptr && p.row_stats_out == nullptr;
+  if (bf16_ln && p.act == kActGelu) return 2;
+  if (bf16_ln && p.act == kActNone) return 3;
+  return 0;
+}
+// process-wide option "resid_epilogue": which specialised epilogue instantiations of the CTA-pair kernel may be used:
+// 0 none (generic kernel), 1 the residual GEMMs, 2 (default) also QKV / FFN-1 with the folded LayerNorm
 int get_option_resid_epilogue();
 
 // CTA-pair (cta_group::2) kernel, gemm_tc2.cu

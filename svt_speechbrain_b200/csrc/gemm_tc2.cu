@@ -400,16 +400,23 @@ int gemm_bf16_tc_pair(const GemmArgs& g, cudaStream_t stream) {
   if (first_use_on_device(attr_seen)) {
     SVT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
     SVT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+    SVT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+    SVT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
   }
   const int m_pairs = ceil_div(g.M, 2 * BM);
   const int n_tiles = g.N / BN2;
   const int units = m_pairs * n_tiles / n_inner;
   const int max_pairs = num_sms() / 2;
   const int grid = 2 * (units < max_pairs ? units : max_pairs);
-  if (gemm_epi_resid_fast(p, g.N) && get_option_resid_epilogue() != 0)
-    gemm_tc2_kernel<1><<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles, n_inner);
-  else
-    gemm_tc2_kernel<0><<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles, n_inner);
+  int epi = gemm_epi_mode(p, g.N);
+  const int opt = get_option_resid_epilogue();  // 0: generic kernel only, 1: residual variant only, 2 (default): all variants
+  if (opt == 0 || (opt == 1 && epi != 1)) epi = 0;
+  switch (epi) {
+    case 1: gemm_tc2_kernel<1><<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles, n_inner); break;
+    case 2: gemm_tc2_kernel<2><<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles, n_inner); break;
+    case 3: gemm_tc2_kernel<3><<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles, n_inner); break;
+    default: gemm_tc2_kernel<0><<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles, n_inner);
+  }
   SVT_POST_LAUNCH();
   return kOk;
 }

@@ -107,13 +107,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
   constexpr int kColsPerWarp = BN / 2;
   // kMode 2 / 3 (own kernel instantiations, gemm_epi_mode() on the host): bf16-only output with the folded LayerNorm and
   // GELU (FFN-1) / no activation (QKV) known at compile time -- no runtime switches in the 32-element chunk body.
-  constexpr bool kFixedBf16 = kMode == 2 || kMode == 3;
+  constexpr bool kFixedBf16 = kMode == 2 || kMode == 3 || kMode == 4;  // 4: bias only (conv GEMMs with the fused row LayerNorm)
   const bool f32_path = !kFixedBf16 && (p.out_f32 != nullptr || p.resid != nullptr || p.resid_bf16 != nullptr ||
                                         p.row_mask != nullptr || p.act == kActPRelu);
-  const int act = kMode == 2 ? static_cast<int>(kActGelu) : (kMode == 3 ? static_cast<int>(kActNone) : p.act);
+  const int act = kMode == 2 ? static_cast<int>(kActGelu) : (kMode == 3 || kMode == 4 ? static_cast<int>(kActNone) : p.act);
   const int c4 = lane & 7;
   const uint32_t bias_slot = stage_addr + 2048, colsum_slot = stage_addr + 2048 + 512;
-  const bool ln = kFixedBf16 || p.ln_stats != nullptr;  // host side guarantees !f32_path and bias != nullptr with it
+  const bool ln = kMode == 2 || kMode == 3 || (kMode == 0 && p.ln_stats != nullptr);  // host side guarantees !f32_path and bias != nullptr with it
   float ln_rstd = 1.f, ln_shift = 0.f;
   if (!f32_path && p.bias != nullptr) {
     if (4 * lane < kColsPerWarp) {
@@ -406,6 +406,7 @@ inline int gemm_epi_mode(const GemmEpiParams& p, int N) {
                        p.rowln_gamma == nullptr && p.row_stats_out == nullptr;
   if (bf16_ln && p.act == kActGelu) return 2;
   if (bf16_ln && p.act == kActNone) return 3;
+  if (p.rowln_gamma != nullptr && p.bias != nullptr) return 4;  // gemm_rowln_supported() has checked the rest
   return 0;
 }
 // process-wide option "resid_epilogue": which specialised epilogue instantiations of the CTA-pair kernel may be used:

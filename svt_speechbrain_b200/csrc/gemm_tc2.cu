@@ -166,7 +166,8 @@ __device__ __forceinline__ void rowln_finish(const GemmEpiParams& p, int row0, i
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-// kEpi: 0 = every epilogue variant, 1 = only the residual path of gemm_epilogue_tile (out-projection / FFN-2)
+// kEpi: 0 = every epilogue variant; 1 = only the residual path of gemm_epilogue_tile (out-projection / FFN-2); 2 / 3 = folded
+// LayerNorm with / without GELU (FFN-1 / QKV); 4 = bias only, with the fused row LayerNorm behind it (conv feature extractor)
 template <int kEpi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmEpiParams p,
@@ -402,6 +403,7 @@ int gemm_bf16_tc_pair(const GemmArgs& g, cudaStream_t stream) {
     SVT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
     SVT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
     SVT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+    SVT_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
   }
   const int m_pairs = ceil_div(g.M, 2 * BM);
   const int n_tiles = g.N / BN2;
@@ -415,6 +417,7 @@ int gemm_bf16_tc_pair(const GemmArgs& g, cudaStream_t stream) {
     case 1: gemm_tc2_kernel<1><<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles, n_inner); break;
     case 2: gemm_tc2_kernel<2><<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles, n_inner); break;
     case 3: gemm_tc2_kernel<3><<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles, n_inner); break;
+    case 4: gemm_tc2_kernel<4><<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles, n_inner); break;
     default: gemm_tc2_kernel<0><<<grid, kThreads, kSmemBytes2, stream>>>(tmA, tmB, p, k_inner, g.K / BK, m_pairs, n_tiles, n_inner);
   }
   SVT_POST_LAUNCH();

@@ -108,6 +108,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
   // kMode 2 / 3 (own kernel instantiations, gemm_epi_mode() on the host): bf16-only output with the folded LayerNorm and
   // GELU (FFN-1) / no activation (QKV) known at compile time -- no runtime switches in the 32-element chunk body.
   constexpr bool kFixedBf16 = kMode == 2 || kMode == 3 || kMode == 4;  // 4: bias only (conv GEMMs with the fused row LayerNorm)
+  // (kMode 5 / 6 take their own branch below and never reach the bias staging of the bf16 path)
   const bool f32_path = !kFixedBf16 && (p.out_f32 != nullptr || p.resid != nullptr || p.resid_bf16 != nullptr ||
                                         p.row_mask != nullptr || p.act == kActPRelu);
   const int act = kMode == 2 ? static_cast<int>(kActGelu) : (kMode == 3 || kMode == 4 ? static_cast<int>(kActNone) : p.act);
@@ -203,6 +204,67 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmEpiParams& p, int r
           *reinterpret_cast<float4*>(of + i * step + c) = a;
           *reinterpret_cast<uint2*>(ob + i * step + c) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
         }
+      }
+      __syncwarp();
+    }
+  } else if constexpr (kMode == 5 || kMode == 6) {
+    // kMode 5 / 6 (one-CTA kernel, the ResNet convolutions of the video stream): out = ring_mask * PReLU(acc + bias
+    // (+ bf16 residual)) as bf16, whole BN-column tiles.  Same order of memory operations as the generic path; row
+    // predicates, the padding-ring mask and the pointers are formed once per tile.
+    const int rbase = quad * 32 + (lane >> 3);
+    uint32_t vmask = 0, keep = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (rbase + 4 * i < valid) {
+        vmask |= 1u << i;
+        if (p.row_mask == nullptr || p.row_mask[static_cast<size_t>(row0 + rbase + 4 * i)] != 0) keep |= 1u << i;
+      }
+    }
+    const size_t ld = static_cast<size_t>(p.ld_out);
+    const size_t base = static_cast<size_t>(row0 + rbase) * ld + static_cast<size_t>(col0 + half * kColsPerWarp + 4 * c4);
+    __nv_bfloat16* ob = p.out_bf16 + base;
+    const __nv_bfloat16* rbp = (kMode == 6) ? p.resid_bf16 + base : nullptr;
+    const float* bp = p.bias + col0 + half * kColsPerWarp + 4 * c4;
+    const float* ap = p.alpha + col0 + half * kColsPerWarp + 4 * c4;
+    const size_t step = 4 * ld;
+    uint32_t rn[32];
+    tmem_ld32(tmem_row, rn);
+#pragma unroll 1
+    for (int c = 0; c < kColsPerWarp; c += 32) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + c));
+      const float4 al = __ldg(reinterpret_cast<const float4*>(ap + c));
+      uint2 rbv[8];
+      if constexpr (kMode == 6) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          rbv[i] = ((vmask >> i) & 1u) ? *reinterpret_cast<const uint2*>(rbp + i * step + c) : make_uint2(0u, 0u);
+      }
+      tmem_ld_wait_regs(rn);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        epi_sts128(stage_addr + lane * 128 + ((q ^ (lane & 7)) << 4), rn[4 * q], rn[4 * q + 1], rn[4 * q + 2], rn[4 * q + 3]);
+      if (c + 32 < kColsPerWarp) tmem_ld32(tmem_row + c + 32, rn);
+      __syncwarp();
+      uint4 raw[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + (lane >> 3);
+        raw[i] = epi_lds128(stage_addr + rr * 128 + ((c4 ^ (rr & 7)) << 4));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 a = make_float4(__uint_as_float(raw[i].x) + b4.x, __uint_as_float(raw[i].y) + b4.y,
+                               __uint_as_float(raw[i].z) + b4.z, __uint_as_float(raw[i].w) + b4.w);
+        if constexpr (kMode == 6) {
+          const __nv_bfloat162 r01 = *reinterpret_cast<const __nv_bfloat162*>(&rbv[i].x);
+          const __nv_bfloat162 r23 = *reinterpret_cast<const __nv_bfloat162*>(&rbv[i].y);
+          a.x += __low2float(r01); a.y += __high2float(r01); a.z += __low2float(r23); a.w += __high2float(r23);
+        }
+        a.x = a.x > 0.f ? a.x : a.x * al.x; a.y = a.y > 0.f ? a.y : a.y * al.y;
+        a.z = a.z > 0.f ? a.z : a.z * al.z; a.w = a.w > 0.f ? a.w : a.w * al.w;
+        if (!((keep >> i) & 1u)) a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((vmask >> i) & 1u)
+          *reinterpret_cast<uint2*>(ob + i * step + c) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
       }
       __syncwarp();
     }

@@ -116,7 +116,9 @@ __device__ __forceinline__ void posconv_epilogue_tile(const GemmEpiParams& p, in
   epi_bar_sync();  // the next tile's phase 0 overwrites the acc tile
 }
 
-template <int BN>
+// kEpi: 0 = every epilogue variant; 5 / 6 = only the PReLU + padding-ring-mask (+ bf16 residual) epilogue of the video
+// stream's ResNet convolutions (gemm_epilogue_tile<BN, kEpi>)
+template <int BN, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KParams p) {
   using C = Cfg<BN>;
@@ -288,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         posconv_epilogue_tile(p.e, clip * p.clip_rows + tt * kPosRows, p.clip_valid - tt * kPosRows, n_tile * p.n_stride, p.n_valid,
                               tmem_base + static_cast<uint32_t>(as * BN), quad, half, lane, smem_u32(stage_area), &tempty_bar[as]);
       } else {
-        gemm_epilogue_tile<BN>(p.e, row0, valid, n_tile * p.n_stride, p.n_valid, tmem_base + static_cast<uint32_t>(as * BN), quad,
+        gemm_epilogue_tile<BN, kEpi>(p.e, row0, valid, n_tile * p.n_stride, p.n_valid, tmem_base + static_cast<uint32_t>(as * BN), quad,
                                half, lane, stage_mine, pf_cur);
         // all of this warp's TMEM reads are complete (wait::ld above) -> release the accumulator stage
         tc_fence_before();
@@ -369,10 +371,20 @@ int launch(const GemmArgs& g, const KParams& kp, cudaStream_t stream) {
   const uint32_t wb[2] = {BK, BN};
   SVT_TRY(encode_bf16_map(&tmB, g.w, 2, wd, ws, wb));
   static std::atomic<unsigned long long> attr_seen{0};
-  if (first_use_on_device(attr_seen)) SVT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  if (first_use_on_device(attr_seen)) {
+    SVT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    SVT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    SVT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  }
   const int tiles = kp.m_tiles * kp.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, kp);
+  // the ResNet convolutions of the video stream (bias + PReLU + padding-ring mask (+ bf16 residual) -> bf16, whole tiles)
+  const bool conv_epi = g.mode == 0 && g.act == kActPRelu && g.alpha != nullptr && g.bias != nullptr && g.out_bf16 != nullptr &&
+                        g.out_f32 == nullptr && g.resid == nullptr && g.row_stats_out == nullptr && g.ln_stats == nullptr &&
+                        g.N % BN == 0 && get_option_resid_epilogue() == 2;
+  if (conv_epi && g.resid_bf16 != nullptr) gemm_tc_kernel<BN, 6><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, kp);
+  else if (conv_epi) gemm_tc_kernel<BN, 5><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, kp);
+  else gemm_tc_kernel<BN, 0><<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, kp);
   SVT_POST_LAUNCH();
   return kOk;
 }

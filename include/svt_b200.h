@@ -52,7 +52,10 @@ long long svt_debug_launch_count(void);
  * 128-column tiles, 3 force the CTA-pair kernel.  "ln_fold": 1 (default) folds the two per-layer LayerNorms of pre-LN
  * (stable_layer_norm) transformer layers into the neighbouring GEMMs, 0 runs them as separate kernels.  "rowln_fuse": 1
  * (default) runs conv -> LayerNorm(512) -> GELU of the layer-norm feature extractors as one kernel per layer
- * (svt_op_gemm_rowln), 0 as a GEMM followed by a LayerNorm kernel. */
+ * (svt_op_gemm_rowln), 0 as a GEMM followed by a LayerNorm kernel.  "conv0_impl": 0 (default) tensor-core first conv layer for
+ * layer-norm models, 1 the SIMT kernel.  "resid_epilogue": which per-configuration epilogue instantiations of the GEMM kernels
+ * may run: 2 (default) all, 1 only the residual GEMMs', 0 the generic kernel (identical results).  "resid_bf16": 1 keeps the
+ * residual stream of the folded pre-LN layers in bf16 only (faster, logits error x 1.6; default 0). */
 int svt_set_option(const char* name, int value);
 
 /* development aid: device buffer of 4 x 256 int64 that CTA 0 of the tcgen05 attention kernel fills with clock64()

@@ -58,3 +58,26 @@ t_f = timeit(lambda: lin(fus(a, v)))
 print(f"AV pipeline B={B} x 10 s: {t_all:.2f} ms/step = {B * 10 / t_all * 1e3:.0f} audio-s/s per GPU "
       f"with the two encoders on two streams, {t_seq:.2f} ms back to back "
       f"(audio lobe {t_a:.2f} ms, video lobe {t_v:.2f} ms, fusion + head {t_f:.2f} ms)")
+
+
+def per_step(fn, n=20, warm=3):
+    """Per-step device times (events around every step) and the host time to ISSUE one step."""
+    import time
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    t0 = time.perf_counter()
+    ev[0].record()
+    for i in range(n):
+        fn()
+        ev[i + 1].record()
+    issue = (time.perf_counter() - t0) / n
+    torch.cuda.synchronize()
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(n))
+    return ts, issue * 1e3
+
+
+ts, issue = per_step(lambda: tr.logits(wav, video))
+print(f"per step: median {ts[len(ts) // 2]:.2f} ms, min {ts[0]:.2f}, max {ts[-1]:.2f}, mean {sum(ts) / len(ts):.2f}; "
+      f"host time per issued step {issue:.2f} ms (a lower bound on nothing: the launch queue throttles the host)", flush=True)
